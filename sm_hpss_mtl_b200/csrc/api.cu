@@ -1,0 +1,736 @@
+// C-ABI layer of libhpss_b200: context / plan caches / batch layouts / fused and host entry
+// points.  Declarations and the reference call each entry replaces: include/hpss_b200.h.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "common.cuh"
+
+namespace hpss {
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_error = buf;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return HPSS_ERR_CUDA;
+}
+
+// ---- host-side tables --------------------------------------------------------------
+static double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+// numpy.linspace(start, stop, num, endpoint=True)
+static void linspace(double start, double stop, int num, std::vector<double>& y) {
+    y.resize(num);
+    if (num == 1) { y[0] = start; return; }
+    const double step = (stop - start) / (double)(num - 1);
+    for (int i = 0; i < num; ++i) y[i] = (double)i * step + start;
+    y[num - 1] = stop;
+}
+
+// librosa.filters.mel(sr, n_fft, n_mels, fmin=0, fmax=sr/2, htk=False, norm='slaney', dtype=float32)
+int build_mel(int sr, int n_fft, int n_mels, float* out) {
+    if (sr <= 0 || n_fft < 2 || n_mels < 1) {
+        set_error("mel: invalid sr=%d n_fft=%d n_mels=%d", sr, n_fft, n_mels);
+        return HPSS_ERR_INVALID;
+    }
+    const int nfreq = 1 + n_fft / 2;
+    std::vector<double> fftfreqs, mels, mel_f(n_mels + 2);
+    linspace(0.0, (double)sr / 2, nfreq, fftfreqs);
+    linspace(hz_to_mel(0.0), hz_to_mel((double)sr / 2), n_mels + 2, mels);
+    for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(mels[i]);
+    for (int i = 0; i < n_mels; ++i) {
+        const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        for (int f = 0; f < nfreq; ++f) {
+            const double lower = -(mel_f[i] - fftfreqs[f]) / fd0;
+            const double upper = (mel_f[i + 2] - fftfreqs[f]) / fd1;
+            const float w = (float)std::max(0.0, std::min(lower, upper));   // stored as float32 ...
+            out[(size_t)i * nfreq + f] = (float)((double)w * enorm);          // ... then *= enorm (f64 -> f32)
+        }
+    }
+    return HPSS_OK;
+}
+
+// scipy.signal.get_window('hann', win, fftbins=True), librosa.util.pad_center to n_fft
+void build_window(int n_fft, int win, float* out) {
+    const int lpad = (n_fft - win) / 2;
+    for (int i = 0; i < n_fft; ++i) out[i] = 0.f;
+    for (int n = 0; n < win; ++n) out[lpad + n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)win));
+}
+
+static int factor_radices(int n2, int* radix, int* n_pass) {
+    int n = n2, np = 0;
+    const int odd[2] = {5, 3};
+    for (int p : odd)
+        while (n % p == 0) { if (np >= kMaxRadixPasses) return -1; radix[np++] = p; n /= p; }
+    while (n % 4 == 0) { if (np >= kMaxRadixPasses) return -1; radix[np++] = 4; n /= 4; }
+    while (n % 2 == 0) { if (np >= kMaxRadixPasses) return -1; radix[np++] = 2; n /= 2; }
+    if (n != 1 || np == 0) return -1;
+    *n_pass = np;
+    return 0;
+}
+
+int get_fft_plan(hpss_ctx* ctx, int n_fft, int win, FftPlan** out) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto key = std::make_pair(n_fft, win);
+    auto it = ctx->fft_plans.find(key);
+    if (it != ctx->fft_plans.end()) { *out = it->second; return HPSS_OK; }
+    if (n_fft < 4 || (n_fft & 1)) {
+        set_error("n_fft=%d must be even and >= 4", n_fft);
+        return HPSS_ERR_UNSUPPORTED;
+    }
+    if (win < 1 || win > n_fft) {
+        set_error("win_length=%d must be in [1, n_fft=%d] (librosa.util.pad_center)", win, n_fft);
+        return HPSS_ERR_INVALID;
+    }
+    FftPlan* p = new FftPlan();
+    p->n_fft = n_fft; p->win = win; p->n2 = n_fft / 2;
+    if (factor_radices(p->n2, p->radix, &p->n_pass)) {
+        delete p;
+        set_error("n_fft=%d: n_fft/2 must factor into 2, 3 and 5", n_fft);
+        return HPSS_ERR_UNSUPPORTED;
+    }
+    std::vector<float> w(n_fft);
+    build_window(n_fft, win, w.data());
+    std::vector<float2> th(p->n2), tf(p->n2 + 1);
+    for (int k = 0; k < p->n2; ++k) {
+        const double a = -2.0 * M_PI * (double)k / (double)p->n2;
+        th[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (int k = 0; k <= p->n2; ++k) {
+        const double a = -2.0 * M_PI * (double)k / (double)n_fft;
+        tf[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    HPSS_CUDA(cudaMalloc(&p->d_window, sizeof(float) * n_fft));
+    HPSS_CUDA(cudaMalloc(&p->d_tw_half, sizeof(float2) * p->n2));
+    HPSS_CUDA(cudaMalloc(&p->d_tw_full, sizeof(float2) * (p->n2 + 1)));
+    HPSS_CUDA(cudaMemcpy(p->d_window, w.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
+    HPSS_CUDA(cudaMemcpy(p->d_tw_half, th.data(), sizeof(float2) * p->n2, cudaMemcpyHostToDevice));
+    HPSS_CUDA(cudaMemcpy(p->d_tw_full, tf.data(), sizeof(float2) * (p->n2 + 1), cudaMemcpyHostToDevice));
+    ctx->fft_plans[key] = p;
+    *out = p;
+    return HPSS_OK;
+}
+
+int get_mel_plan(hpss_ctx* ctx, int sr, int n_fft, int n_mels, MelPlan** out) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto key = std::make_tuple(sr, n_fft, n_mels);
+    auto it = ctx->mel_plans.find(key);
+    if (it != ctx->mel_plans.end()) { *out = it->second; return HPSS_OK; }
+    const int rows = 1 + n_fft / 2;
+    std::vector<float> w((size_t)n_mels * rows);
+    int rc = build_mel(sr, n_fft, n_mels, w.data());
+    if (rc) return rc;
+    std::vector<int2> band(n_mels);
+    for (int m = 0; m < n_mels; ++m) {
+        int first = rows, last = 0;
+        for (int f = 0; f < rows; ++f)
+            if (w[(size_t)m * rows + f] != 0.f) { first = std::min(first, f); last = f + 1; }
+        if (first >= last) first = last = 0;
+        band[m] = make_int2(first, last);
+    }
+    MelPlan* p = new MelPlan();
+    p->sr = sr; p->n_fft = n_fft; p->n_mels = n_mels; p->rows = rows;
+    HPSS_CUDA(cudaMalloc(&p->d_w, sizeof(float) * w.size()));
+    HPSS_CUDA(cudaMalloc(&p->d_band, sizeof(int2) * n_mels));
+    HPSS_CUDA(cudaMemcpy(p->d_w, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+    HPSS_CUDA(cudaMemcpy(p->d_band, band.data(), sizeof(int2) * n_mels, cudaMemcpyHostToDevice));
+    ctx->mel_plans[key] = p;
+    *out = p;
+    return HPSS_OK;
+}
+
+int ensure_workspace(hpss_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return HPSS_OK;
+    if (ctx->ws) {
+        HPSS_CUDA(cudaDeviceSynchronize());   // rare: only when the workspace has to grow
+        HPSS_CUDA(cudaFree(ctx->ws));
+        ctx->ws = nullptr;
+        ctx->ws_bytes = 0;
+    }
+    const size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&ctx->ws, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&ctx->ws, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("out of device memory: workspace of %zu bytes", bytes);
+            return HPSS_ERR_NOMEM;
+        }
+        ctx->ws_bytes = bytes;
+        return HPSS_OK;
+    }
+    ctx->ws_bytes = want;
+    return HPSS_OK;
+}
+
+int ensure_stft_tiles(hpss_batch* b, int tt) {
+    if (b->stft_tt == tt && (b->d_stft_tiles || b->n_stft_tiles == 0)) return HPSS_OK;
+    std::vector<int2> tiles;
+    for (int c = 0; c < b->n_clips; ++c) {
+        const int64_t T = b->frame_off[c + 1] - b->frame_off[c];
+        for (int64_t t0 = 0; t0 < T; t0 += tt) tiles.push_back(make_int2(c, (int)t0));
+    }
+    if (b->d_stft_tiles) { HPSS_CUDA(cudaFree(b->d_stft_tiles)); b->d_stft_tiles = nullptr; }
+    b->n_stft_tiles = (int)tiles.size();
+    b->stft_tt = tt;
+    if (!tiles.empty()) {
+        HPSS_CUDA(cudaMalloc(&b->d_stft_tiles, sizeof(int2) * tiles.size()));
+        HPSS_CUDA(cudaMemcpy(b->d_stft_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice));
+    }
+    return HPSS_OK;
+}
+
+static int make_batch(hpss_ctx* ctx, const std::vector<int64_t>& samples, const std::vector<int64_t>& frames,
+                      bool has_samples, int n_fft, int hop, hpss_batch** out) {
+    const int n = (int)frames.size();
+    hpss_batch* b = new hpss_batch();
+    b->ctx = ctx; b->n_clips = n; b->n_fft = n_fft; b->hop = hop; b->has_samples = has_samples;
+    b->sample_off.assign(n + 1, 0);
+    b->frame_off.assign(n + 1, 0);
+    for (int c = 0; c < n; ++c) {
+        b->sample_off[c + 1] = b->sample_off[c] + (has_samples ? samples[c] : 0);
+        b->frame_off[c + 1] = b->frame_off[c] + frames[c];
+        b->max_frames = std::max(b->max_frames, frames[c]);
+    }
+    cudaError_t e = cudaMalloc(&b->d_frame_off, sizeof(int64_t) * (n + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_sample_off, sizeof(int64_t) * (n + 1));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(b->d_frame_off, b->frame_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(b->d_sample_off, b->sample_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (b->d_frame_off) cudaFree(b->d_frame_off);
+        if (b->d_sample_off) cudaFree(b->d_sample_off);
+        delete b;
+        return cuda_fail(e, "batch offsets");
+    }
+    *out = b;
+    return HPSS_OK;
+}
+
+static int feature_streams(int feature) { return feature >= HPSS_FEAT_HARMPERC ? 2 : 1; }
+static bool feature_is_mel(int feature) {
+    return feature == HPSS_FEAT_MELSPEC || feature == HPSS_FEAT_LOGMELSPEC || feature == HPSS_FEAT_MEL_HARMPERC ||
+           feature == HPSS_FEAT_LOGMEL_HARMPERC;
+}
+static bool feature_is_log(int feature) {
+    return feature == HPSS_FEAT_LOGSPEC || feature == HPSS_FEAT_LOGMELSPEC || feature == HPSS_FEAT_LOG_HARMPERC ||
+           feature == HPSS_FEAT_LOGMEL_HARMPERC;
+}
+
+static int check_params(const hpss_params* p) {
+    if (!p) { set_error("params is NULL"); return HPSS_ERR_INVALID; }
+    if (p->feature < HPSS_FEAT_SPEC || p->feature > HPSS_FEAT_LOGMEL_HARMPERC) {
+        set_error("unknown feature id %d", p->feature);
+        return HPSS_ERR_INVALID;
+    }
+    if (feature_is_mel(p->feature) && (p->n_mels < 1 || p->mel_sr < 1)) {
+        set_error("feature %d needs n_mels >= 1 and mel_sr >= 1 (got %d, %d)", p->feature, p->n_mels, p->mel_sr);
+        return HPSS_ERR_INVALID;
+    }
+    if (feature_streams(p->feature) == 2 && (p->l_harm < 1 || p->l_perc < 1)) {
+        set_error("l_harm=%d / l_perc=%d must be >= 1", p->l_harm, p->l_perc);
+        return HPSS_ERR_INVALID;
+    }
+    if (feature_is_log(p->feature) && !(p->amin > 0.f)) {
+        set_error("amin must be strictly positive (librosa.power_to_db)");
+        return HPSS_ERR_INVALID;
+    }
+    return HPSS_OK;
+}
+
+// spectrogram -> features (everything after the STFT); S may alias nothing in the workspace
+static int features_from_spec(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, const hpss_params* p,
+                              float* harm, float* perc, uint32_t* clip_max, float* out, cudaStream_t st) {
+    const int ns = feature_streams(p->feature);
+    const bool is_mel = feature_is_mel(p->feature), is_log = feature_is_log(p->feature);
+    MelPlan* mp = nullptr;
+    int rc;
+    if (is_mel) {
+        rc = get_mel_plan(ctx, p->mel_sr, 2 * (rows - 1), p->n_mels, &mp);
+        if (rc) return rc;
+    }
+    if (ns == 2) {
+        rc = launch_median(ctx, b, S, rows, p->l_harm, true, harm, st);
+        if (rc) return rc;
+        rc = launch_median(ctx, b, S, rows, p->l_perc, false, perc, st);
+        if (rc) return rc;
+    }
+    const int pre_square = (ns == 1 && is_mel) ? 1 : 0;   // melspectrogram(y=..) uses |X|^2
+    const bool clip = is_log && p->top_db >= 0.f;
+    rc = launch_mask_mel(ctx, b, S, ns == 2 ? harm : nullptr, ns == 2 ? perc : nullptr, rows,
+                         mp ? mp->d_w : nullptr, mp ? mp->d_band : nullptr, mp ? mp->n_mels : 0, pre_square,
+                         is_log ? 1 : 0, p->amin, out, clip ? clip_max : nullptr, st);
+    if (rc) return rc;
+    if (clip) {
+        rc = launch_topdb(ctx, b, out, is_mel ? p->n_mels : rows, ns, clip_max, p->top_db, st);
+        if (rc) return rc;
+    }
+    return HPSS_OK;
+}
+
+struct Workspace {
+    float* S; float* harm; float* perc; uint32_t* clip_max;
+};
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static int carve_workspace(hpss_ctx* ctx, const hpss_batch* b, int rows, bool need_S, bool need_hp, size_t extra,
+                           Workspace* w, void** extra_ptr) {
+    const size_t n = (size_t)rows * (size_t)b->frame_off[b->n_clips];
+    const size_t sz = align256(n * sizeof(float));
+    const size_t cm = align256(sizeof(uint32_t) * 2 * (size_t)std::max(1, b->n_clips));
+    const size_t total = (need_S ? sz : 0) + (need_hp ? 2 * sz : 0) + cm + align256(extra);
+    int rc = ensure_workspace(ctx, total);
+    if (rc) return rc;
+    char* p = (char*)ctx->ws;
+    w->S = nullptr; w->harm = nullptr; w->perc = nullptr;
+    if (need_S) { w->S = (float*)p; p += sz; }
+    if (need_hp) { w->harm = (float*)p; p += sz; w->perc = (float*)p; p += sz; }
+    w->clip_max = (uint32_t*)p; p += cm;
+    if (extra_ptr) *extra_ptr = p;
+    return HPSS_OK;
+}
+
+static int featuregram_device(hpss_ctx* ctx, hpss_batch* b, const float* wave, const hpss_params* p, float* out,
+                              cudaStream_t st) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!b->has_samples) { set_error("batch was built from frame counts; waveform entry needs sample lengths"); return HPSS_ERR_INVALID; }
+    if (b->n_fft != p->n_fft || b->hop != p->hop_length) {
+        set_error("batch was laid out for n_fft=%d hop=%d, params say %d / %d", b->n_fft, b->hop, p->n_fft, p->hop_length);
+        return HPSS_ERR_INVALID;
+    }
+    FftPlan* plan = nullptr;
+    rc = get_fft_plan(ctx, p->n_fft, p->win_length, &plan);
+    if (rc) return rc;
+    const int rows = p->n_fft / 2 + 1;
+    if (p->feature == HPSS_FEAT_SPEC) return launch_stft(ctx, b, wave, plan, p->hop_length, 0, out, nullptr, st);
+    Workspace w;
+    rc = carve_workspace(ctx, b, rows, true, feature_streams(p->feature) == 2, 0, &w, nullptr);
+    if (rc) return rc;
+    rc = launch_stft(ctx, b, wave, plan, p->hop_length, 0, w.S, nullptr, st);
+    if (rc) return rc;
+    return features_from_spec(ctx, b, w.S, rows, p, w.harm, w.perc, w.clip_max, out, st);
+}
+
+}  // namespace hpss
+
+using namespace hpss;
+
+// =====================================================================================
+extern "C" {
+
+const char* hpss_version(void) { return "hpss_b200 0.1 (sm_100a)"; }
+const char* hpss_last_error(void) { return t_error.c_str(); }
+uint64_t hpss_launch_count(void) { return g_launches.load(); }
+
+int hpss_ctx_create(int device, hpss_ctx** out) {
+    if (!out) { set_error("ctx out pointer is NULL"); return HPSS_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return HPSS_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { set_error("device %d out of range [0,%d)", device, n); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(device));
+    hpss_ctx* ctx = new hpss_ctx();
+    ctx->device = device;
+    cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (ctx->sm_count <= 0) ctx->sm_count = kSMs;
+    *out = ctx;
+    return HPSS_OK;
+}
+
+int hpss_ctx_destroy(hpss_ctx* ctx) {
+    if (!ctx) return HPSS_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : ctx->fft_plans) {
+        cudaFree(kv.second->d_window); cudaFree(kv.second->d_tw_half); cudaFree(kv.second->d_tw_full);
+        delete kv.second;
+    }
+    for (auto& kv : ctx->mel_plans) { cudaFree(kv.second->d_w); cudaFree(kv.second->d_band); delete kv.second; }
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->band_scratch) cudaFree(ctx->band_scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pipe_dev[i]) cudaFree(ctx->pipe_dev[i]);
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
+        if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
+    }
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    delete ctx;
+    return HPSS_OK;
+}
+
+int hpss_ctx_device(const hpss_ctx* ctx) { return ctx ? ctx->device : -1; }
+uint64_t hpss_ctx_workspace_bytes(const hpss_ctx* ctx) { return ctx ? ctx->ws_bytes + 2 * ctx->pipe_bytes : 0; }
+
+int hpss_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) { set_error("ptr is NULL"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return HPSS_OK;
+}
+int hpss_host_free(void* ptr) {
+    if (ptr) HPSS_CUDA(cudaFreeHost(ptr));
+    return HPSS_OK;
+}
+
+int hpss_batch_from_samples(hpss_ctx* ctx, const int64_t* clip_len, int32_t n_clips, int32_t n_fft, int32_t hop,
+                            hpss_batch** out) {
+    if (!ctx || !out || n_clips < 0 || (n_clips > 0 && !clip_len)) { set_error("batch_from_samples: bad arguments"); return HPSS_ERR_INVALID; }
+    if (n_fft < 1 || hop < 1) { set_error("n_fft=%d and hop_length=%d must be positive", n_fft, hop); return HPSS_ERR_INVALID; }
+    std::vector<int64_t> s(n_clips), f(n_clips);
+    for (int c = 0; c < n_clips; ++c) {
+        if (clip_len[c] < n_fft) {
+            set_error("n_fft=%d is too large for input signal of length=%lld (clip %d)", n_fft, (long long)clip_len[c], c);
+            return HPSS_ERR_SHORT_SIGNAL;
+        }
+        s[c] = clip_len[c];
+        f[c] = 1 + (clip_len[c] - n_fft) / hop;
+    }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return make_batch(ctx, s, f, true, n_fft, hop, out);
+}
+
+int hpss_batch_from_frames(hpss_ctx* ctx, const int64_t* clip_frames, int32_t n_clips, hpss_batch** out) {
+    if (!ctx || !out || n_clips < 0 || (n_clips > 0 && !clip_frames)) { set_error("batch_from_frames: bad arguments"); return HPSS_ERR_INVALID; }
+    std::vector<int64_t> s, f(n_clips);
+    for (int c = 0; c < n_clips; ++c) {
+        if (clip_frames[c] < 0 || clip_frames[c] > 0x7fffffff) { set_error("clip %d: frame count %lld out of range", c, (long long)clip_frames[c]); return HPSS_ERR_INVALID; }
+        f[c] = clip_frames[c];
+    }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return make_batch(ctx, s, f, false, 0, 0, out);
+}
+
+int hpss_batch_destroy(hpss_batch* b) {
+    if (!b) return HPSS_OK;
+    cudaSetDevice(b->ctx->device);
+    cudaDeviceSynchronize();
+    if (b->d_frame_off) cudaFree(b->d_frame_off);
+    if (b->d_sample_off) cudaFree(b->d_sample_off);
+    if (b->d_stft_tiles) cudaFree(b->d_stft_tiles);
+    if (b->d_clip_class) cudaFree(b->d_clip_class);
+    for (auto* s : b->host_chunks) hpss_batch_destroy(s);
+    delete b;
+    return HPSS_OK;
+}
+int32_t hpss_batch_n_clips(const hpss_batch* b) { return b ? b->n_clips : 0; }
+int64_t hpss_batch_total_frames(const hpss_batch* b) { return b ? b->frame_off[b->n_clips] : 0; }
+int64_t hpss_batch_total_samples(const hpss_batch* b) { return b ? b->sample_off[b->n_clips] : 0; }
+int hpss_batch_frame_offsets(const hpss_batch* b, int64_t* o) {
+    if (!b || !o) { set_error("frame_offsets: NULL argument"); return HPSS_ERR_INVALID; }
+    memcpy(o, b->frame_off.data(), sizeof(int64_t) * (b->n_clips + 1));
+    return HPSS_OK;
+}
+int hpss_batch_sample_offsets(const hpss_batch* b, int64_t* o) {
+    if (!b || !o) { set_error("sample_offsets: NULL argument"); return HPSS_ERR_INVALID; }
+    memcpy(o, b->sample_off.data(), sizeof(int64_t) * (b->n_clips + 1));
+    return HPSS_OK;
+}
+
+int hpss_mel_filterbank(int32_t sr, int32_t n_fft, int32_t n_mels, float* out) {
+    if (!out) { set_error("out is NULL"); return HPSS_ERR_INVALID; }
+    return build_mel(sr, n_fft, n_mels, out);
+}
+int hpss_stft_window(int32_t n_fft, int32_t win, float* out) {
+    if (!out || win < 1 || win > n_fft) { set_error("stft_window: need 1 <= win_length <= n_fft"); return HPSS_ERR_INVALID; }
+    build_window(n_fft, win, out);
+    return HPSS_OK;
+}
+
+int hpss_stft_mag(hpss_ctx* ctx, const hpss_batch* batch, const float* wave, int32_t n_fft, int32_t win,
+                  int32_t hop, int32_t power, float* S, float* cplx, void* stream) {
+    if (!ctx || !batch || !wave || !S) { set_error("stft_mag: NULL argument"); return HPSS_ERR_INVALID; }
+    if (!batch->has_samples || batch->n_fft != n_fft || batch->hop != hop) {
+        set_error("stft_mag: batch layout (n_fft=%d hop=%d) does not match call (n_fft=%d hop=%d)", batch->n_fft,
+                  batch->hop, n_fft, hop);
+        return HPSS_ERR_INVALID;
+    }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    FftPlan* plan = nullptr;
+    int rc = get_fft_plan(ctx, n_fft, win, &plan);
+    if (rc) return rc;
+    return launch_stft(ctx, const_cast<hpss_batch*>(batch), wave, plan, hop, power, S, cplx, (cudaStream_t)stream);
+}
+
+int hpss_median_time(hpss_ctx* ctx, const hpss_batch* batch, const float* S, int32_t rows, int32_t k, float* out,
+                     void* stream) {
+    if (!ctx || !batch || !S || !out || S == out) { set_error("median_time: NULL or aliased argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return launch_median(ctx, batch, S, rows, k, true, out, (cudaStream_t)stream);
+}
+int hpss_median_freq(hpss_ctx* ctx, const hpss_batch* batch, const float* S, int32_t rows, int32_t k, float* out,
+                     void* stream) {
+    if (!ctx || !batch || !S || !out || S == out) { set_error("median_freq: NULL or aliased argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return launch_median(ctx, batch, S, rows, k, false, out, (cudaStream_t)stream);
+}
+
+int hpss_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* S, const float* harm, const float* perc,
+                      int32_t rows, const float* mel, int32_t n_mels, int32_t pre_square, int32_t log_power,
+                      float amin, float* out, uint32_t* clip_max, void* stream) {
+    if (!ctx || !batch || !S || !out) { set_error("mask_mel_log: NULL argument"); return HPSS_ERR_INVALID; }
+    if ((harm == nullptr) != (perc == nullptr)) { set_error("mask_mel_log: harm and perc must both be given or both NULL"); return HPSS_ERR_INVALID; }
+    if (rows < 1 || (mel && n_mels < 1)) { set_error("mask_mel_log: rows=%d n_mels=%d", rows, n_mels); return HPSS_ERR_INVALID; }
+    if (log_power && !(amin > 0.f)) { set_error("amin must be strictly positive (librosa.power_to_db)"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int2* band = nullptr;
+    if (mel) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->band_scratch_n < n_mels) {
+            if (ctx->band_scratch) { HPSS_CUDA(cudaDeviceSynchronize()); HPSS_CUDA(cudaFree(ctx->band_scratch)); ctx->band_scratch = nullptr; }
+            HPSS_CUDA(cudaMalloc(&ctx->band_scratch, sizeof(int2) * n_mels));
+            ctx->band_scratch_n = n_mels;
+        }
+        band = ctx->band_scratch;
+        int rc = launch_mel_bands(mel, n_mels, rows, band, st);
+        if (rc) return rc;
+    }
+    return launch_mask_mel(ctx, batch, S, harm, perc, rows, mel, band, n_mels, pre_square, log_power, amin, out,
+                           clip_max, st);
+}
+
+int hpss_topdb_clip(hpss_ctx* ctx, const hpss_batch* batch, float* out, int32_t rows_per_stream, int32_t n_streams,
+                    const uint32_t* clip_max, float top_db, void* stream) {
+    if (!ctx || !batch || !out || !clip_max) { set_error("topdb_clip: NULL argument"); return HPSS_ERR_INVALID; }
+    if (top_db < 0.f) { set_error("top_db must be non-negative (librosa.power_to_db)"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return launch_topdb(ctx, batch, out, rows_per_stream, n_streams, clip_max, top_db, (cudaStream_t)stream);
+}
+
+int32_t hpss_feature_rows(const hpss_params* p) {
+    if (!p) return -1;
+    const int ns = feature_streams(p->feature);
+    return ns * (feature_is_mel(p->feature) ? p->n_mels : p->n_fft / 2 + 1);
+}
+
+int hpss_featuregram(hpss_ctx* ctx, const hpss_batch* batch, const float* wave, const hpss_params* p, float* out,
+                     void* stream) {
+    if (!ctx || !batch || !wave || !out) { set_error("featuregram: NULL argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return featuregram_device(ctx, const_cast<hpss_batch*>(batch), wave, p, out, (cudaStream_t)stream);
+}
+
+int hpss_featuregram_from_spec(hpss_ctx* ctx, const hpss_batch* batch, const float* S, int32_t rows,
+                               const hpss_params* p, float* out, void* stream) {
+    if (!ctx || !batch || !S || !out) { set_error("featuregram_from_spec: NULL argument"); return HPSS_ERR_INVALID; }
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (rows < 2) { set_error("rows=%d", rows); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->feature == HPSS_FEAT_SPEC) {
+        HPSS_CUDA(cudaMemcpyAsync(out, S, sizeof(float) * (size_t)rows * batch->frame_off[batch->n_clips],
+                                  cudaMemcpyDeviceToDevice, st));
+        return HPSS_OK;
+    }
+    Workspace w;
+    rc = carve_workspace(ctx, batch, rows, false, feature_streams(p->feature) == 2, 0, &w, nullptr);
+    if (rc) return rc;
+    return features_from_spec(ctx, batch, S, rows, p, w.harm, w.perc, w.clip_max, out, st);
+}
+
+// Host-buffer entry: clips are cut into chunks; chunk i+1 uploads while chunk i computes and
+// chunk i-1 downloads (three streams, two device slots).
+int hpss_featuregram_host(hpss_ctx* ctx, const hpss_batch* batch, const float* wave_host, const hpss_params* p,
+                          float* out_host) {
+    if (!ctx || !batch || !wave_host || !out_host) { set_error("featuregram_host: NULL argument"); return HPSS_ERR_INVALID; }
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!batch->has_samples) { set_error("featuregram_host needs a batch built from sample lengths"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->s_h2d) {
+        HPSS_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        HPSS_CUDA(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+        HPSS_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            HPSS_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+            HPSS_CUDA(cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+            HPSS_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    hpss_batch* pb = const_cast<hpss_batch*>(batch);
+    const int n = batch->n_clips;
+    const int rows_out = hpss_feature_rows(p);
+    if (pb->host_cut.empty()) {
+        // chunking: ~16 chunks, at least 4 M samples each, never splitting a clip
+        const int64_t total_samples = batch->sample_off[n];
+        const int64_t target = std::max<int64_t>(total_samples / 16, 4 << 20);
+        std::vector<int> cut(1, 0);
+        for (int c = 0; c < n;) {
+            int e = c;
+            int64_t acc = 0;
+            while (e < n && (e == c || acc + (batch->sample_off[e + 1] - batch->sample_off[e]) <= target)) {
+                acc += batch->sample_off[e + 1] - batch->sample_off[e];
+                ++e;
+            }
+            cut.push_back(e);
+            c = e;
+        }
+        std::vector<hpss_batch*> subs(cut.size() - 1, nullptr);
+        for (size_t i = 0; i + 1 < cut.size(); ++i) {
+            std::vector<int64_t> len(cut[i + 1] - cut[i]);
+            for (int c = cut[i]; c < cut[i + 1]; ++c) len[c - cut[i]] = batch->sample_off[c + 1] - batch->sample_off[c];
+            rc = hpss_batch_from_samples(ctx, len.data(), (int)len.size(), batch->n_fft, batch->hop, &subs[i]);
+            if (rc) { for (auto* s : subs) if (s) hpss_batch_destroy(s); return rc; }
+        }
+        pb->host_cut = cut;
+        pb->host_chunks = subs;
+    }
+    const std::vector<int>& cut = pb->host_cut;
+    const std::vector<hpss_batch*>& subs = pb->host_chunks;
+    const int n_chunks = (int)cut.size() - 1;
+    size_t max_w = 0, max_o = 0;
+    for (int i = 0; i < n_chunks; ++i) {
+        max_w = std::max(max_w, (size_t)(batch->sample_off[cut[i + 1]] - batch->sample_off[cut[i]]));
+        max_o = std::max(max_o, (size_t)rows_out * (size_t)(batch->frame_off[cut[i + 1]] - batch->frame_off[cut[i]]));
+    }
+    const size_t slot_bytes = align256(max_w * sizeof(float)) + align256(max_o * sizeof(float));
+    if (slot_bytes > ctx->pipe_bytes) {
+        HPSS_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->pipe_dev[i]) { HPSS_CUDA(cudaFree(ctx->pipe_dev[i])); ctx->pipe_dev[i] = nullptr; }
+            HPSS_CUDA(cudaMalloc(&ctx->pipe_dev[i], slot_bytes));
+        }
+        ctx->pipe_bytes = slot_bytes;
+    }
+    auto cleanup = [&]() {};
+    // the shared compute workspace must be sized for the largest chunk before the pipeline starts
+    {
+        size_t need = 0;
+        const int rows = p->n_fft / 2 + 1;
+        for (int i = 0; i < n_chunks; ++i) {
+            const size_t sz = align256((size_t)rows * (size_t)subs[i]->frame_off[subs[i]->n_clips] * sizeof(float));
+            need = std::max(need, 3 * sz + align256(sizeof(uint32_t) * 2 * (size_t)std::max(1, subs[i]->n_clips)));
+        }
+        rc = ensure_workspace(ctx, need);
+        if (rc) { cleanup(); return rc; }
+    }
+    for (int i = 0; i < n_chunks; ++i) {
+        const int s = i & 1;
+        float* d_wave = (float*)ctx->pipe_dev[s];
+        float* d_out = (float*)((char*)ctx->pipe_dev[s] + align256(max_w * sizeof(float)));
+        const size_t ws = (size_t)(batch->sample_off[cut[i + 1]] - batch->sample_off[cut[i]]);
+        const size_t os = (size_t)rows_out * (size_t)(batch->frame_off[cut[i + 1]] - batch->frame_off[cut[i]]);
+        cudaError_t e = cudaSuccess;
+        if (i >= 2) e = cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[s], 0);      // wave slot free
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(d_wave, wave_host + batch->sample_off[cut[i]], ws * sizeof(float),
+                                cudaMemcpyHostToDevice, ctx->s_h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_h2d[s], ctx->s_h2d);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[s], 0);
+        if (e == cudaSuccess && i >= 2) e = cudaStreamWaitEvent(ctx->s_comp, ctx->ev_d2h[s], 0);   // out slot free
+        if (e != cudaSuccess) { cudaDeviceSynchronize(); cleanup(); return cuda_fail(e, "host pipeline (upload)"); }
+        rc = featuregram_device(ctx, subs[i], d_wave, p, d_out, ctx->s_comp);
+        if (rc) { cudaDeviceSynchronize(); cleanup(); return rc; }
+        e = cudaEventRecord(ctx->ev_comp[s], ctx->s_comp);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[s], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(out_host + (size_t)rows_out * (size_t)batch->frame_off[cut[i]], d_out,
+                                os * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_d2h);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_d2h[s], ctx->s_d2h);
+        if (e != cudaSuccess) { cudaDeviceSynchronize(); cleanup(); return cuda_fail(e, "host pipeline (download)"); }
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->s_d2h);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_comp);
+    cleanup();
+    if (e != cudaSuccess) return cuda_fail(e, "host pipeline (sync)");
+    return HPSS_OK;
+}
+
+int hpss_moments(hpss_ctx* ctx, const hpss_batch* batch, const float* feat, int32_t D, const int32_t* clip_class,
+                 int32_t n_classes, double* sum, double* sumsq, double* count, double* nonfinite, void* stream) {
+    if (!ctx || !batch || !feat || !clip_class || !sum || !sumsq || !count || !nonfinite) { set_error("moments: NULL argument"); return HPSS_ERR_INVALID; }
+    if (D < 1 || n_classes < 1) { set_error("moments: D=%d n_classes=%d", D, n_classes); return HPSS_ERR_INVALID; }
+    for (int c = 0; c < batch->n_clips; ++c)
+        if (clip_class[c] < 0 || clip_class[c] >= n_classes) { set_error("moments: clip %d has class %d outside [0,%d)", c, clip_class[c], n_classes); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    hpss_batch* b = const_cast<hpss_batch*>(batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!b->d_clip_class && b->n_clips > 0) HPSS_CUDA(cudaMalloc(&b->d_clip_class, sizeof(int32_t) * b->n_clips));
+    if (b->n_clips > 0)
+        HPSS_CUDA(cudaMemcpyAsync(b->d_clip_class, clip_class, sizeof(int32_t) * b->n_clips, cudaMemcpyHostToDevice, st));
+    return launch_moments(ctx, batch, feat, D, b->d_clip_class, n_classes, sum, sumsq, count, nonfinite, st);
+}
+
+int hpss_stats_finalize(const double* sum, const double* sumsq, const double* count, int32_t D, int32_t n_classes,
+                        float* mean_out, float* stdev_out) {
+    if (!sum || !sumsq || !count || !mean_out || !stdev_out || D < 1 || n_classes < 1) { set_error("stats_finalize: bad argument"); return HPSS_ERR_INVALID; }
+    double N = 0;
+    for (int k = 0; k < n_classes; ++k) N += count[k];
+    for (int d = 0; d < D; ++d) {
+        double mu = 0, tot = 0;
+        for (int k = 0; k < n_classes; ++k) {
+            mu += sum[(size_t)k * D + d] / (count[k] + 1e-10);   // class mean (:530-532)
+            tot += sum[(size_t)k * D + d];
+        }
+        mu /= (double)n_classes;                                  // unweighted mean of class means (:533-536)
+        const double ss = sumsq[d] - 2.0 * mu * tot + N * mu * mu;   // sum (x - mu)^2
+        mean_out[d] = (float)mu;
+        stdev_out[d] = (float)sqrt(std::max(ss, 0.0) / (N - 1.0));
+    }
+    return HPSS_OK;
+}
+
+int hpss_scale_data(hpss_ctx* ctx, const hpss_batch* batch, const float* feat, int32_t D, const float* mean,
+                    const float* stdev, double eps, double* out, void* stream) {
+    if (!ctx || !batch || !feat || !mean || !stdev || !out) { set_error("scale_data: NULL argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return launch_scale(ctx, batch, feat, D, mean, stdev, eps, out, (cudaStream_t)stream);
+}
+
+int hpss_row_standardize(hpss_ctx* ctx, const hpss_batch* batch, float* feat, int32_t D, void* stream) {
+    if (!ctx || !batch || !feat || D < 1) { set_error("row_standardize: bad argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return launch_row_standardize(ctx, batch, feat, D, (cudaStream_t)stream);
+}
+
+int64_t hpss_num_patches(int64_t n_frames, int32_t W, int32_t shift) {
+    if (W < 1 || shift < 1) return 0;
+    const int64_t half = W / 2;
+    const int64_t a = half, b = n_frames - half;
+    return b > a ? (b - a + shift - 1) / shift : 0;
+}
+
+int hpss_extract_patches(hpss_ctx* ctx, const float* feat, int32_t D, int64_t T, int32_t W, int32_t shift,
+                         double* out, void* stream) {
+    if (!ctx || !feat || !out || D < 1 || W < 1 || shift < 1) { set_error("extract_patches: bad argument"); return HPSS_ERR_INVALID; }
+    if (T < W) { set_error("extract_patches: %lld frames < patch_size %d (caller tiles the clip first, lib/preprocessing.py:139-142)", (long long)T, W); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return launch_patches(feat, D, T, W, shift, hpss_num_patches(T, W, shift), out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

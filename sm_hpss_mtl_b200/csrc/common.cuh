@@ -1,0 +1,160 @@
+// Internal declarations shared by the kernels and the C-ABI layer of libhpss_b200.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "../../include/hpss_b200.h"
+
+namespace hpss {
+
+constexpr int kSMs = 148;               // B200: 2 dies x 74 SMs
+constexpr int kMaxRadixPasses = 16;
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+extern std::atomic<uint64_t> g_launches;
+
+#define HPSS_CUDA(x)                                              \
+    do {                                                          \
+        cudaError_t e_ = (x);                                     \
+        if (e_ != cudaSuccess) return ::hpss::cuda_fail(e_, #x);  \
+    } while (0)
+
+#define HPSS_LAUNCHED(name)                                           \
+    do {                                                              \
+        ::hpss::g_launches.fetch_add(1, std::memory_order_relaxed);   \
+        cudaError_t e_ = cudaGetLastError();                          \
+        if (e_ != cudaSuccess) return ::hpss::cuda_fail(e_, name);    \
+    } while (0)
+
+// ---- plans ------------------------------------------------------------------------
+struct FftPlan {
+    int n_fft = 0, win = 0, n2 = 0;
+    int n_pass = 0;
+    int radix[kMaxRadixPasses] = {0};
+    float* d_window = nullptr;   // n_fft floats (periodic Hann, centre padded)
+    float2* d_tw_half = nullptr; // n2 entries exp(-2 pi i k / n2)
+    float2* d_tw_full = nullptr; // n2+1 entries exp(-2 pi i k / n_fft)
+};
+
+struct MelPlan {
+    int sr = 0, n_fft = 0, n_mels = 0, rows = 0;
+    float* d_w = nullptr;        // dense (n_mels, rows)
+    int2* d_band = nullptr;      // per filter [first, last+1) non-zero column
+};
+
+}  // namespace hpss
+
+struct hpss_ctx {
+    int device = 0;
+    std::mutex mu;
+    std::map<std::pair<int, int>, hpss::FftPlan*> fft_plans;
+    std::map<std::tuple<int, int, int>, hpss::MelPlan*> mel_plans;
+    // grow-only device workspace (S, harm, perc, clip_max, band scratch)
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    int2* band_scratch = nullptr;
+    int band_scratch_n = 0;
+    // host pipeline
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    void* pipe_dev[2] = {nullptr, nullptr};   // double-buffered wave + feature staging
+    size_t pipe_bytes = 0;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    int max_smem_optin = 0;
+    int sm_count = hpss::kSMs;
+};
+
+struct hpss_batch {
+    hpss_ctx* ctx = nullptr;
+    int n_clips = 0;
+    int n_fft = 0, hop = 0;
+    bool has_samples = false;
+    std::vector<int64_t> sample_off;   // n_clips + 1
+    std::vector<int64_t> frame_off;    // n_clips + 1
+    int64_t max_frames = 0;
+    int64_t* d_sample_off = nullptr;
+    int64_t* d_frame_off = nullptr;
+    // K1 tile list (clip, first frame), built for a given tile height
+    int stft_tt = 0;
+    int n_stft_tiles = 0;
+    int2* d_stft_tiles = nullptr;
+    int32_t* d_clip_class = nullptr;   // scratch for hpss_moments
+    // clip chunks of the pipelined host entry (built on first use, owned by this batch)
+    std::vector<int> host_cut;
+    std::vector<hpss_batch*> host_chunks;
+};
+
+namespace hpss {
+
+int get_fft_plan(hpss_ctx* ctx, int n_fft, int win, FftPlan** out);
+int get_mel_plan(hpss_ctx* ctx, int sr, int n_fft, int n_mels, MelPlan** out);
+int ensure_workspace(hpss_ctx* ctx, size_t bytes);
+int ensure_stft_tiles(hpss_batch* b, int tt);
+
+// host-side table builders (double precision)
+int build_mel(int sr, int n_fft, int n_mels, float* out);
+void build_window(int n_fft, int win, float* out);
+
+// stage launchers (device pointers, enqueue on stream)
+int launch_stft(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* plan, int hop,
+                int power, float* S, float* cplx, cudaStream_t st);
+int launch_median(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, int k, bool time_axis,
+                  float* out, cudaStream_t st);
+int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm,
+                    const float* perc, int rows, const float* mel, const int2* band, int n_mels,
+                    int pre_square, int log_power, float amin, float* out, uint32_t* clip_max,
+                    cudaStream_t st);
+int launch_mel_bands(const float* mel, int n_mels, int rows, int2* band, cudaStream_t st);
+int launch_topdb(hpss_ctx* ctx, const hpss_batch* b, float* out, int rows_per_stream, int n_streams,
+                 const uint32_t* clip_max, float top_db, cudaStream_t st);
+int launch_moments(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, const int32_t* d_class,
+                   int n_classes, double* sum, double* sumsq, double* count, double* nonfinite,
+                   cudaStream_t st);
+int launch_scale(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, const float* mean,
+                 const float* stdev, double eps, double* out, cudaStream_t st);
+int launch_row_standardize(hpss_ctx* ctx, const hpss_batch* b, float* feat, int D, cudaStream_t st);
+int launch_patches(const float* feat, int D, int64_t T, int W, int shift, int64_t n_patches, double* out,
+                   cudaStream_t st);
+
+// ---- device helpers ---------------------------------------------------------------
+#ifdef __CUDACC__
+// scipy.ndimage 'reflect' (half-sample symmetric), valid for any overshoot.
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    if ((unsigned)i < (unsigned)n) return i;          // interior: no reflection
+    if (i < 0 && i >= -n) return -1 - i;              // one reflection at the left border
+    if (i >= n && i < 2 * n) return 2 * n - 1 - i;    // one reflection at the right border
+    const int p = 2 * n;
+    i %= p;
+    if (i < 0) i += p;
+    return i < n ? i : p - 1 - i;
+}
+
+// largest c with off[c] <= g  (off has n+1 entries, off[0] == 0, off[n] == total)
+__device__ __forceinline__ int find_clip(const int64_t* __restrict__ off, int n, int64_t g) {
+    int lo = 0, hi = n;   // invariant: off[lo] <= g < off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// order-preserving float <-> uint mapping for atomicMax on floats of either sign
+__device__ __forceinline__ uint32_t float_to_ordered(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t k) {
+    const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+#endif
+
+}  // namespace hpss

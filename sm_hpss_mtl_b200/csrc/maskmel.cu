@@ -1,0 +1,264 @@
+// K3 / K3b: soft masks + masked spectrogram + banded mel projection + power_to_db.
+//
+// Replaces, per clip, the tail of librosa.decompose.hpss (util.softmask(power=2,
+// split_zeros=True) twice and S*mask), librosa.feature.melspectrogram(S=., n_mels=M)
+// (np.dot with the Slaney basis) and librosa.core.power_to_db(.**2)
+// (lib/preprocessing.py:408-412, 418-424, 430-434, 440-444 of the reference).
+//
+// The soft-mask arithmetic uses the IEEE round-to-nearest intrinsics in numpy's operation
+// order (no FMA contraction), so H = S*mask_h and P = S*mask_p are bit-identical to the
+// reference for identical (S, harm, perc).  The mel basis is banded (triangles): only the
+// [first,last) non-zero columns of each filter are visited, in increasing f, fp32 FMA.
+//
+// One CTA owns 32 consecutive frames of the batch (lane = frame, so every global access is
+// a coalesced 128-byte row segment); the 8 warps split the frequency rows (mask phase) and
+// the mel filters (projection phase); masked values are staged through shared memory in
+// chunks of 64 frequency rows.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace hpss {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kFC = 64;   // frequency rows staged per chunk
+
+struct FrameLane {
+    bool valid;
+    int clip;
+    int T;
+    int64_t in_base;    // + f*T
+    int64_t out_base;   // + row*T
+};
+
+__device__ __forceinline__ FrameLane frame_lane(const int64_t* __restrict__ frame_off, int n_clips, int64_t total,
+                                                int64_t gf, int rows_in, int rows_out) {
+    FrameLane fl;
+    fl.valid = gf < total;
+    fl.clip = 0; fl.T = 1; fl.in_base = 0; fl.out_base = 0;
+    if (fl.valid) {
+        const int c = find_clip(frame_off, n_clips, gf);
+        const int64_t fo = __ldg(frame_off + c);
+        fl.clip = c;
+        fl.T = (int)(__ldg(frame_off + c + 1) - fo);
+        fl.in_base = (int64_t)rows_in * fo + (gf - fo);
+        fl.out_base = (int64_t)rows_out * fo + (gf - fo);
+    }
+    return fl;
+}
+
+// numpy op order of librosa.util.softmask(power=2, split_zeros=True) and S*mask.
+__device__ __forceinline__ void softmask_apply(float s, float h, float p, float& H, float& P) {
+    const float zmax = fmaxf(h, p);
+    const bool bad = zmax < FLT_MIN;
+    const float Z = bad ? 1.0f : zmax;
+    const float qh = __fdiv_rn(h, Z);
+    const float qp = __fdiv_rn(p, Z);
+    const float mh = __fmul_rn(qh, qh);
+    const float mp = __fmul_rn(qp, qp);
+    const float den = __fadd_rn(mh, mp);
+    const float mask_h = bad ? 0.5f : __fdiv_rn(mh, den);
+    const float mask_p = bad ? 0.5f : __fdiv_rn(mp, den);
+    H = __fmul_rn(s, mask_h);
+    P = __fmul_rn(s, mask_p);
+}
+
+__device__ __forceinline__ float post_value(float x, int log_power, float amin) {
+    if (!log_power) return x;
+    const float x2 = __fmul_rn(x, x);
+    return 10.0f * log10f(fmaxf(amin, x2));
+}
+
+// per-(clip, stream) running max -> global ordered-uint atomicMax, one atomic per
+// distinct clip in the warp
+__device__ __forceinline__ void publish_max(uint32_t* __restrict__ clip_max, int n_streams, int stream, bool valid,
+                                            int clip, float v) {
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    const unsigned peers = __match_any_sync(active, clip);
+    const uint32_t key = __reduce_max_sync(peers, float_to_ordered(v));
+    if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicMax(clip_max + (size_t)n_streams * clip + stream, key);
+}
+
+template <bool HPSS_MODE>
+__global__ void __launch_bounds__(kThreads)
+mask_mel_kernel(const float* __restrict__ S, const float* __restrict__ harm, const float* __restrict__ perc,
+                const int64_t* __restrict__ frame_off, int n_clips, int64_t total_frames, int rows,
+                const float* __restrict__ mel, const int2* __restrict__ band, int n_mels, int pre_square,
+                int log_power, float amin, float* __restrict__ out, uint32_t* __restrict__ clip_max) {
+    constexpr int NS = HPSS_MODE ? 2 : 1;
+    extern __shared__ float smem[];
+    __shared__ float s_max[NS][kWarps][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool project = mel != nullptr;
+    const int rows_out = NS * (project ? n_mels : rows);
+    const FrameLane fl = frame_lane(frame_off, n_clips, total_frames, (int64_t)blockIdx.x * 32 + lane, rows, rows_out);
+
+    float vmax[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) vmax[s] = -INFINITY;
+
+    if (!project) {
+        // identity projection: [H; P] (or plain S) rows, optional power_to_db
+        for (int f = warp; f < rows; f += kWarps) {
+            if (!fl.valid) continue;
+            const int64_t gi = fl.in_base + (int64_t)f * fl.T;
+            float sv = __ldg(S + gi);
+            if (HPSS_MODE) {
+                float H, P;
+                softmask_apply(sv, __ldg(harm + gi), __ldg(perc + gi), H, P);
+                const float a = post_value(H, log_power, amin), b = post_value(P, log_power, amin);
+                out[fl.out_base + (int64_t)f * fl.T] = a;
+                out[fl.out_base + (int64_t)(rows + f) * fl.T] = b;
+                vmax[0] = fmaxf(vmax[0], a);
+                vmax[NS - 1] = fmaxf(vmax[NS - 1], b);
+            } else {
+                if (pre_square) sv = __fmul_rn(sv, sv);
+                const float a = post_value(sv, log_power, amin);
+                out[fl.out_base + (int64_t)f * fl.T] = a;
+                vmax[0] = fmaxf(vmax[0], a);
+            }
+        }
+    } else {
+        float* Hc = smem;                       // [kFC][32]
+        float* Pc = Hc + kFC * 32;              // [kFC][32]   (HPSS mode only)
+        float* acc = HPSS_MODE ? Pc + kFC * 32 : Pc;   // [NS][n_mels][32]
+        for (int i = threadIdx.x; i < NS * n_mels * 32; i += kThreads) acc[i] = 0.f;
+        for (int f0 = 0; f0 < rows; f0 += kFC) {
+            const int fe = min(rows, f0 + kFC);
+            // phase 1: masked values of this chunk -> shared memory
+            for (int f = f0 + warp; f < fe; f += kWarps) {
+                float H = 0.f, P = 0.f;
+                if (fl.valid) {
+                    const int64_t gi = fl.in_base + (int64_t)f * fl.T;
+                    const float sv = __ldg(S + gi);
+                    if (HPSS_MODE) softmask_apply(sv, __ldg(harm + gi), __ldg(perc + gi), H, P);
+                    else H = pre_square ? __fmul_rn(sv, sv) : sv;
+                }
+                Hc[(f - f0) * 32 + lane] = H;
+                if (HPSS_MODE) Pc[(f - f0) * 32 + lane] = P;
+            }
+            __syncthreads();
+            // phase 2: banded projection of the chunk
+            for (int m = warp; m < n_mels; m += kWarps) {
+                const int2 bd = __ldg(band + m);
+                const int a = max(bd.x, f0), b = min(bd.y, fe);
+                if (a >= b) continue;
+                float sh = 0.f, sp = 0.f;
+                const float* w = mel + (size_t)m * rows;
+                for (int f = a; f < b; ++f) {
+                    const float wf = __ldg(w + f);
+                    sh = fmaf(wf, Hc[(f - f0) * 32 + lane], sh);
+                    if (HPSS_MODE) sp = fmaf(wf, Pc[(f - f0) * 32 + lane], sp);
+                }
+                acc[m * 32 + lane] += sh;
+                if (HPSS_MODE) acc[(n_mels + m) * 32 + lane] += sp;
+            }
+            __syncthreads();
+        }
+        for (int r = warp; r < NS * n_mels; r += kWarps) {
+            if (!fl.valid) continue;
+            const float a = post_value(acc[r * 32 + lane], log_power, amin);
+            out[fl.out_base + (int64_t)r * fl.T] = a;
+            const int s = (NS == 2 && r >= n_mels) ? 1 : 0;
+            vmax[s] = fmaxf(vmax[s], a);
+        }
+    }
+
+    if (clip_max != nullptr) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) s_max[s][warp][lane] = vmax[s];
+        __syncthreads();
+        if (warp < NS) {
+            float v = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) v = fmaxf(v, s_max[warp][w][lane]);
+            publish_max(clip_max, NS, warp, fl.valid, fl.clip, v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+topdb_kernel(float* __restrict__ out, const int64_t* __restrict__ frame_off, int n_clips, int64_t total_frames,
+             int rows_per_stream, int n_streams, const uint32_t* __restrict__ clip_max, float top_db) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rows = rows_per_stream * n_streams;
+    const FrameLane fl = frame_lane(frame_off, n_clips, total_frames, (int64_t)blockIdx.x * 32 + lane, rows, rows);
+    if (!fl.valid) return;
+    for (int s = 0; s < n_streams; ++s) {
+        const float thr = ordered_to_float(__ldg(clip_max + (size_t)n_streams * fl.clip + s)) - top_db;
+        for (int r = warp; r < rows_per_stream; r += kWarps) {
+            float* p = out + fl.out_base + (int64_t)(s * rows_per_stream + r) * fl.T;
+            *p = fmaxf(*p, thr);
+        }
+    }
+}
+
+__global__ void mel_band_kernel(const float* __restrict__ mel, int n_mels, int rows, int2* __restrict__ band) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mels) return;
+    int first = rows, last = 0;
+    for (int f = 0; f < rows; ++f) {
+        if (mel[(size_t)m * rows + f] != 0.f) {
+            if (f < first) first = f;
+            last = f + 1;
+        }
+    }
+    if (first >= last) { first = 0; last = 0; }
+    band[m] = make_int2(first, last);
+}
+
+}  // namespace
+
+int launch_mel_bands(const float* mel, int n_mels, int rows, int2* band, cudaStream_t st) {
+    mel_band_kernel<<<(n_mels + 127) / 128, 128, 0, st>>>(mel, n_mels, rows, band);
+    HPSS_LAUNCHED("mel_band_kernel");
+    return HPSS_OK;
+}
+
+int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, const float* perc,
+                    int rows, const float* mel, const int2* band, int n_mels, int pre_square, int log_power,
+                    float amin, float* out, uint32_t* clip_max, cudaStream_t st) {
+    const int64_t total = b->frame_off[b->n_clips];
+    const bool hpss_mode = harm != nullptr;
+    const int ns = hpss_mode ? 2 : 1;
+    if (clip_max) HPSS_CUDA(cudaMemsetAsync(clip_max, 0, sizeof(uint32_t) * (size_t)ns * b->n_clips, st));
+    if (total == 0) return HPSS_OK;
+    size_t smem = 0;
+    if (mel) smem = ((size_t)ns * kFC * 32 + (size_t)ns * n_mels * 32) * sizeof(float);
+    if (smem > (size_t)ctx->max_smem_optin) {
+        set_error("n_mels=%d needs %zu bytes of shared memory (max %d)", n_mels, smem, ctx->max_smem_optin);
+        return HPSS_ERR_UNSUPPORTED;
+    }
+    const unsigned grid = (unsigned)((total + 31) / 32);
+    if (hpss_mode) {
+        HPSS_CUDA(cudaFuncSetAttribute(mask_mel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mask_mel_kernel<true><<<grid, kThreads, smem, st>>>(S, harm, perc, b->d_frame_off, b->n_clips, total, rows,
+                                                            mel, band, n_mels, pre_square, log_power, amin, out,
+                                                            clip_max);
+    } else {
+        HPSS_CUDA(cudaFuncSetAttribute(mask_mel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mask_mel_kernel<false><<<grid, kThreads, smem, st>>>(S, nullptr, nullptr, b->d_frame_off, b->n_clips, total,
+                                                             rows, mel, band, n_mels, pre_square, log_power, amin,
+                                                             out, clip_max);
+    }
+    HPSS_LAUNCHED("mask_mel_kernel");
+    return HPSS_OK;
+}
+
+int launch_topdb(hpss_ctx* ctx, const hpss_batch* b, float* out, int rows_per_stream, int n_streams,
+                 const uint32_t* clip_max, float top_db, cudaStream_t st) {
+    (void)ctx;
+    const int64_t total = b->frame_off[b->n_clips];
+    if (total == 0) return HPSS_OK;
+    const unsigned grid = (unsigned)((total + 31) / 32);
+    topdb_kernel<<<grid, kThreads, 0, st>>>(out, b->d_frame_off, b->n_clips, total, rows_per_stream, n_streams,
+                                            clip_max, top_db);
+    HPSS_LAUNCHED("topdb_kernel");
+    return HPSS_OK;
+}
+
+}  // namespace hpss

@@ -1,0 +1,213 @@
+// K5 + N1: feature moments for get_data_stats, scale_data, per-clip row standardisation
+// (sklearn StandardScaler as used by get_feature_patches) and the patch gather of
+// lib/cython_impl/tools.pyx:extract_patches.
+//
+// Reference: lib/preprocessing.py:461-586 (two-pass corpus statistics), :590-614 and
+// tools.pyx:138-166 (scale_data), :137-292 + tools.pyx:21-38 (patches).
+#include "common.cuh"
+
+namespace hpss {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Raw moments.  Persistent CTAs walk tiles of 32 frames; per (row, tile) a warp reduces its
+// 32 lanes in float64 and adds into CTA-private shared accumulators; one float64 atomicAdd
+// per accumulator and CTA at the end.
+__global__ void __launch_bounds__(kThreads)
+moments_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_off, int n_clips,
+               int64_t total_frames, int D, const int32_t* __restrict__ clip_class, int n_classes,
+               double* __restrict__ g_sum, double* __restrict__ g_sumsq, double* __restrict__ g_count,
+               double* __restrict__ g_nonfinite) {
+    extern __shared__ double sacc[];   // [n_classes][D] sums, then [D] sumsq
+    double* s_sum = sacc;
+    double* s_sq = sacc + (size_t)n_classes * D;
+    __shared__ unsigned long long s_bad;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (n_classes + 1) * D; i += kThreads) sacc[i] = 0.0;
+    if (threadIdx.x == 0) s_bad = 0ull;
+    __syncthreads();
+
+    unsigned long long bad = 0;
+    const int64_t n_tiles = (total_frames + 31) / 32;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t gf = tile * 32 + lane;
+        const bool valid = gf < total_frames;
+        int cls = -1, T = 1;
+        int64_t base = 0;
+        if (valid) {
+            const int c = find_clip(frame_off, n_clips, gf);
+            const int64_t fo = __ldg(frame_off + c);
+            T = (int)(__ldg(frame_off + c + 1) - fo);
+            base = (int64_t)D * fo + (gf - fo);
+            cls = __ldg(clip_class + c);
+        }
+        const int cls0 = __shfl_sync(0xffffffffu, cls, 0);
+        const bool uniform = __all_sync(0xffffffffu, cls == cls0 || !valid);
+        for (int d = warp; d < D; d += kWarps) {
+            float x = 0.f;
+            if (valid) {
+                x = __ldg(feat + base + (int64_t)d * T);
+                if (!isfinite(x)) { x = 0.f; ++bad; }
+            }
+            const double xd = (double)x;
+            const double sq = warp_sum(xd * xd);
+            if (uniform) {
+                const double s = warp_sum(xd);
+                if (lane == 0) { s_sum[(size_t)cls0 * D + d] += s; s_sq[d] += sq; }
+            } else {
+                for (int k = 0; k < n_classes; ++k) {
+                    const double s = warp_sum(cls == k ? xd : 0.0);
+                    if (lane == 0) s_sum[(size_t)k * D + d] += s;
+                }
+                if (lane == 0) s_sq[d] += sq;
+            }
+        }
+    }
+    if (bad) atomicAdd(&s_bad, bad);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_classes * D; i += kThreads)
+        if (s_sum[i] != 0.0) atomicAdd(g_sum + i, s_sum[i]);
+    for (int i = threadIdx.x; i < D; i += kThreads)
+        if (s_sq[i] != 0.0) atomicAdd(g_sumsq + i, s_sq[i]);
+    if (threadIdx.x == 0 && s_bad) atomicAdd(g_nonfinite, (double)s_bad);
+    // frame counts per class (clip granularity)
+    for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < n_clips; c += (int64_t)gridDim.x * kThreads) {
+        const double T = (double)(frame_off[c + 1] - frame_off[c]);
+        atomicAdd(g_count + clip_class[c], T);
+    }
+}
+
+// (x - mean) / (stdev + eps) in float64, lane = frame
+__global__ void __launch_bounds__(kThreads)
+scale_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_off, int n_clips, int64_t total_frames,
+             int D, const float* __restrict__ mean, const float* __restrict__ stdev, double eps,
+             double* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gf = (int64_t)blockIdx.x * 32 + lane;
+    if (gf >= total_frames) return;
+    const int c = find_clip(frame_off, n_clips, gf);
+    const int64_t fo = __ldg(frame_off + c);
+    const int T = (int)(__ldg(frame_off + c + 1) - fo);
+    const int64_t base = (int64_t)D * fo + (gf - fo);
+    for (int d = warp; d < D; d += kWarps) {
+        const int64_t g = base + (int64_t)d * T;
+        out[g] = ((double)__ldg(feat + g) - (double)__ldg(mean + d)) / ((double)__ldg(stdev + d) + eps);
+    }
+}
+
+// sklearn.preprocessing.StandardScaler(copy=False).fit_transform on one clip's rows:
+// float64 two-pass mean / variance (ddof=0), constant rows keep scale 1, then the in-place
+// float32 updates X -= mean; X /= scale (each evaluated in float64 and rounded to float32).
+// One warp per (clip, row) line.
+__global__ void __launch_bounds__(kThreads)
+row_standardize_kernel(float* __restrict__ feat, const int64_t* __restrict__ frame_off, int n_clips, int D) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_lines = (int64_t)n_clips * D;
+    for (int64_t line = (int64_t)blockIdx.x * kWarps + warp; line < n_lines; line += (int64_t)gridDim.x * kWarps) {
+        const int c = (int)(line / D);
+        const int d = (int)(line - (int64_t)c * D);
+        const int64_t fo = __ldg(frame_off + c);
+        const int T = (int)(__ldg(frame_off + c + 1) - fo);
+        if (T <= 0) continue;
+        float* x = feat + (int64_t)D * fo + (int64_t)d * T;
+        double s = 0.0;
+        for (int t = lane; t < T; t += 32) s += (double)x[t];
+        const double mean = warp_sum(s) / (double)T;
+        double v = 0.0;
+        for (int t = lane; t < T; t += 32) {
+            const double dlt = (double)x[t] - mean;
+            v += dlt * dlt;
+        }
+        const double var = warp_sum(v) / (double)T;
+        const double eps = 2.220446049250313e-16;
+        const double ub = (double)T * eps * var + ((double)T * mean * eps) * ((double)T * mean * eps);
+        const double scale = (var <= ub) ? 1.0 : sqrt(var);
+        for (int t = lane; t < T; t += 32) {
+            const float x1 = (float)((double)x[t] - mean);
+            x[t] = (float)((double)x1 / scale);
+        }
+    }
+}
+
+// patches[p, d, w] = feat[d, start_p + w] as float64 (tools.pyx:21-38)
+__global__ void __launch_bounds__(kThreads)
+patches_kernel(const float* __restrict__ feat, int D, int64_t T, int W, int shift, int64_t n_patches,
+               double* __restrict__ out) {
+    const int64_t total = n_patches * D * (int64_t)W;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const int w = (int)(i % W);
+        const int64_t pd = i / W;
+        const int d = (int)(pd % D);
+        const int64_t p = pd / D;
+        int64_t start = p * shift;
+        int64_t end = start + W;
+        if (end > T) end = T;
+        if (end - start < W) start = end - W;
+        out[i] = (double)__ldg(feat + (int64_t)d * T + start + w);
+    }
+}
+
+}  // namespace
+
+int launch_moments(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, const int32_t* d_class,
+                   int n_classes, double* sum, double* sumsq, double* count, double* nonfinite, cudaStream_t st) {
+    const int64_t total = b->frame_off[b->n_clips];
+    if (total == 0) return HPSS_OK;
+    const size_t smem = (size_t)(n_classes + 1) * D * sizeof(double);
+    if (smem > (size_t)ctx->max_smem_optin) {
+        set_error("moments: D=%d x classes=%d does not fit shared memory", D, n_classes);
+        return HPSS_ERR_UNSUPPORTED;
+    }
+    HPSS_CUDA(cudaFuncSetAttribute(moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t n_tiles = (total + 31) / 32;
+    int64_t grid = (int64_t)ctx->sm_count * 4;
+    if (grid > n_tiles) grid = n_tiles;
+    moments_kernel<<<(unsigned)grid, kThreads, smem, st>>>(feat, b->d_frame_off, b->n_clips, total, D, d_class,
+                                                           n_classes, sum, sumsq, count, nonfinite);
+    HPSS_LAUNCHED("moments_kernel");
+    return HPSS_OK;
+}
+
+int launch_scale(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, const float* mean,
+                 const float* stdev, double eps, double* out, cudaStream_t st) {
+    (void)ctx;
+    const int64_t total = b->frame_off[b->n_clips];
+    if (total == 0) return HPSS_OK;
+    scale_kernel<<<(unsigned)((total + 31) / 32), kThreads, 0, st>>>(feat, b->d_frame_off, b->n_clips, total, D, mean,
+                                                                     stdev, eps, out);
+    HPSS_LAUNCHED("scale_kernel");
+    return HPSS_OK;
+}
+
+int launch_row_standardize(hpss_ctx* ctx, const hpss_batch* b, float* feat, int D, cudaStream_t st) {
+    const int64_t n_lines = (int64_t)b->n_clips * D;
+    if (n_lines == 0) return HPSS_OK;
+    int64_t grid = (n_lines + kWarps - 1) / kWarps;
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    row_standardize_kernel<<<(unsigned)grid, kThreads, 0, st>>>(feat, b->d_frame_off, b->n_clips, D);
+    HPSS_LAUNCHED("row_standardize_kernel");
+    return HPSS_OK;
+}
+
+int launch_patches(const float* feat, int D, int64_t T, int W, int shift, int64_t n_patches, double* out,
+                   cudaStream_t st) {
+    const int64_t total = n_patches * D * (int64_t)W;
+    if (total <= 0) return HPSS_OK;
+    int64_t grid = (total + kThreads - 1) / kThreads;
+    if (grid > kSMs * 16) grid = kSMs * 16;
+    patches_kernel<<<(unsigned)grid, kThreads, 0, st>>>(feat, D, T, W, shift, n_patches, out);
+    HPSS_LAUNCHED("patches_kernel");
+    return HPSS_OK;
+}
+
+}  // namespace hpss

@@ -1,0 +1,252 @@
+"""GPU parity tests: every stage of the CUDA path against the CPU oracle, through the C ABI.
+
+Bars (BASELINE.json north_star): medians and frame indexing bit-exact; soft-masked spectrograms
+bit-exact given identical (S, harm, perc); STFT / features within 1e-4 relative L2 (max-abs
+reported in the assertion message).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import librosa_restated as lr
+from oracle import preprocessing_oracle as po
+from sm_hpss_mtl_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_TOL = 1e-4     # north_star: "librosa-matching features within 1e-4 relative L2"
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def to_dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def flat_batch(mats):
+    """list of (rows, T_c) arrays -> flat float32 batch array."""
+    return np.concatenate([np.ascontiguousarray(m, dtype=np.float32).ravel() for m in mats]) if mats else np.zeros(0, np.float32)
+
+
+# ------------------------------------------------------------------------------ medians
+MEDIAN_CASES = [
+    # (rows, [T_c...], k)
+    (201, [98], 31), (201, [98, 98, 98], 31), (201, [998], 21), (201, [998], 11),
+    (201, [8], 21), (5, [8], 31), (40, [16], 16),           # multi-reflection, even k (generic path)
+    (257, [300, 7, 131, 64], 17), (65, [33, 1, 2, 250], 63),
+    (1025, [120], 31), (33, [70], 3), (33, [70], 5), (33, [70], 64), (17, [50], 101),
+]
+
+
+@pytest.mark.parametrize("rows,Ts,k", MEDIAN_CASES)
+def test_median_bit_exact(ctx, rows, Ts, k):
+    rng = np.random.default_rng(rows * 1000 + k)
+    mats = [np.abs(rng.standard_normal((rows, T))).astype(np.float32) for T in Ts]
+    # ties: quantise a part of the data
+    mats = [np.where(rng.random(m.shape) < 0.3, np.round(m * 4) / 4, m).astype(np.float32) for m in mats]
+    batch = engine.Batch(ctx, clip_frames=Ts)
+    S = to_dev(flat_batch(mats))
+    harm = engine.median_time(batch, S, rows, k)
+    perc = engine.median_freq(batch, S, rows, k)
+    torch.cuda.synchronize()
+    for c, (h, p) in enumerate(zip(batch.split(harm, rows), batch.split(perc, rows))):
+        want_h = lr.median_filter_scipy(mats[c], k, axis=1)
+        want_p = lr.median_filter_scipy(mats[c], k, axis=0)
+        assert np.array_equal(h.cpu().numpy(), want_h), f"time-axis median differs (clip {c}, k={k})"
+        assert np.array_equal(p.cpu().numpy(), want_p), f"freq-axis median differs (clip {c}, k={k})"
+
+
+def test_median_all_fast_kernel_sizes(ctx):
+    rows, T = 70, 75
+    rng = np.random.default_rng(5)
+    m = np.abs(rng.standard_normal((rows, T))).astype(np.float32)
+    batch = engine.Batch(ctx, clip_frames=[T])
+    S = to_dev(m.ravel())
+    for k in range(1, 66):
+        h = engine.median_time(batch, S, rows, k).cpu().numpy().reshape(rows, T)
+        p = engine.median_freq(batch, S, rows, k).cpu().numpy().reshape(rows, T)
+        assert np.array_equal(h, lr.median_filter_scipy(m, k, axis=1)), k
+        assert np.array_equal(p, lr.median_filter_scipy(m, k, axis=0)), k
+
+
+# ------------------------------------------------------------------------------ STFT
+STFT_CASES = [
+    # (n_fft, win, hop, [L...])
+    (400, 400, 160, [16000]), (400, 400, 160, [16000, 400, 559, 560, 3000]),
+    (512, 400, 160, [16000, 8000]), (512, 512, 128, [9000]), (1024, 1024, 256, [20000]),
+    (2048, 2048, 512, [40000]), (240, 200, 80, [5000]), (600, 600, 150, [7000]),
+]
+
+
+@pytest.mark.parametrize("n_fft,win,hop,Ls", STFT_CASES)
+def test_stft_matches_oracle(ctx, n_fft, win, hop, Ls):
+    waves = [synth.synth_clip(i, L) for i, L in enumerate(Ls)]
+    batch = engine.Batch(ctx, clip_lengths=Ls, n_fft=n_fft, hop_length=hop)
+    S, cplx = engine.stft_mag(batch, to_dev(np.concatenate(waves)), n_fft, win, hop, return_complex=True)
+    torch.cuda.synchronize()
+    F = n_fft // 2 + 1
+    for c, y in enumerate(waves):
+        want = lr.stft(y, n_fft=n_fft, hop_length=hop, win_length=win)
+        assert batch.frames(c) == want.shape[1] == 1 + (len(y) - n_fft) // hop      # frame indexing exact
+        got_c = batch.clip(cplx, F, c).cpu().numpy()
+        got_m = batch.clip(S, F, c).cpu().numpy()
+        e_c, e_m = rel_l2(got_c, want), rel_l2(got_m, np.abs(want))
+        maxabs = float(np.abs(got_m - np.abs(want)).max())
+        assert e_c < 1e-5 and e_m < 1e-5, f"rel-L2 complex {e_c:.2e} mag {e_m:.2e} max-abs {maxabs:.2e}"
+
+
+def test_stft_short_signal_raises(ctx):
+    from sm_hpss_mtl_b200._lib import ParameterError
+    with pytest.raises(ParameterError):
+        engine.Batch(ctx, clip_lengths=[399], n_fft=400, hop_length=160)      # librosa: n_fft > len(y)
+    with pytest.raises(lr.ParameterError):
+        lr.stft(np.zeros(399, np.float32), n_fft=400, hop_length=160, win_length=400)
+
+
+def test_stft_unsupported_nfft(ctx):
+    from sm_hpss_mtl_b200._lib import HpssError
+    batch = engine.Batch(ctx, clip_lengths=[4000], n_fft=14 * 2, hop_length=7)
+    with pytest.raises(HpssError):
+        engine.stft_mag(batch, torch.zeros(4000, device="cuda"), 28, 28, 7)     # 14 = 2 * 7
+
+
+# ------------------------------------------------------------------------------ masks
+@pytest.mark.parametrize("rows,Ts,kh,kp", [(201, [98, 60], 31, 31), (201, [300], 21, 11), (257, [120], 17, 17)])
+def test_softmask_bit_exact(ctx, rows, Ts, kh, kp):
+    n_fft = 2 * (rows - 1)
+    mats = []
+    for i, T in enumerate(Ts):
+        y = synth.synth_clip(10 + i, n_fft + 160 * (T - 1))
+        mats.append(np.abs(lr.stft(y, n_fft=n_fft, hop_length=160, win_length=min(400, n_fft))))
+    mats[0][3:6, 4:9] = 0.0             # exact zeros -> split_zeros branch (mask 0.5)
+    batch = engine.Batch(ctx, clip_frames=Ts)
+    S = to_dev(flat_batch(mats))
+    harm = engine.median_time(batch, S, rows, kh)
+    perc = engine.median_freq(batch, S, rows, kp)
+    out, _ = engine.mask_mel_log(batch, S, harm, perc, rows)
+    torch.cuda.synchronize()
+    for c, o in enumerate(batch.split(out, 2 * rows)):
+        H, P = lr.hpss(mats[c], kernel_size=(kh, kp))
+        got = o.cpu().numpy()
+        assert np.array_equal(got[:rows], H), "harmonic masked spectrogram not bit-exact"
+        assert np.array_equal(got[rows:], P), "percussive masked spectrogram not bit-exact"
+
+
+def test_all_zero_input_gives_half_mask(ctx):
+    rows, T = 201, 40
+    batch = engine.Batch(ctx, clip_frames=[T])
+    S = torch.zeros(rows * T, device="cuda")
+    one = torch.ones(rows * T, device="cuda")
+    out, _ = engine.mask_mel_log(batch, one, S, S, rows)     # harm = perc = 0 -> mask 0.5 -> 0.5 * S
+    assert torch.equal(out, torch.full_like(out, 0.5))
+
+
+# ------------------------------------------------------------------------------ mel table
+@pytest.mark.parametrize("sr,n_fft,n_mels", [(22050, 400, 120), (16000, 400, 120), (22050, 512, 21), (22050, 2048, 128)])
+def test_mel_table_matches_oracle(sr, n_fft, n_mels):
+    got = engine.mel_filterbank(sr, n_fft, n_mels)
+    want = lr.mel(sr, n_fft, n_mels)
+    assert got.shape == want.shape
+    assert float(np.abs(got - want).max()) <= 1e-7
+    assert np.array_equal(got > 0, want > 0)
+
+
+# ------------------------------------------------------------------------------ featuregrams
+FEATS = [("Spec", "SPEC"), ("LogSpec", "LOGSPEC"), ("MelSpec", "MELSPEC"), ("LogMelSpec", "LOGMELSPEC"),
+         ("HarmPercSpec", "HARMPERC"), ("LogHarmPercSpec", "LOG_HARMPERC"), ("MelHarmPercSpec", "MEL_HARMPERC"),
+         ("LogMelHarmPercSpec", "LOGMEL_HARMPERC")]
+
+
+@pytest.mark.parametrize("featName,fid", FEATS)
+@pytest.mark.parametrize("n_fft,lh,lp,n_mels", [(400, 21, 11, 120), (512, 31, 31, 21)])
+def test_featuregram_matches_oracle(ctx, featName, fid, n_fft, lh, lp, n_mels):
+    fs, Tw, Ts = 16000, 25, 10
+    Ls = [16000, 48000, 1600, 7777]
+    waves = [synth.synth_clip(100 + i, L) for i, L in enumerate(Ls)]
+    mel_sr = fs if fid in ("MELSPEC", "LOGMELSPEC") else 22050
+    prm = engine.make_params(n_fft=n_fft, win_length=400, hop_length=160, l_harm=lh, l_perc=lp, n_mels=n_mels,
+                             mel_sr=mel_sr, feature=fid)
+    batch = engine.Batch(ctx, clip_lengths=Ls, n_fft=n_fft, hop_length=160)
+    out = engine.featuregram(batch, to_dev(np.concatenate(waves)), prm)
+    torch.cuda.synchronize()
+    rows = engine.feature_rows(prm)
+    for c, y in enumerate(waves):
+        want = po.featuregram(y, fs, Tw, Ts, lh, lp, n_fft, n_mels, featName)
+        got = batch.clip(out, rows, c).cpu().numpy()
+        assert got.shape == want.shape and got.dtype == np.float32
+        err, maxabs = rel_l2(got, want), float(np.abs(got - want).max())
+        assert err < REL_L2_TOL, f"{featName} clip {c}: rel-L2 {err:.3e} (max-abs {maxabs:.3e})"
+
+
+def test_featuregram_host_equals_device(ctx):
+    Ls = [16000] * 37 + [5000, 123456]
+    waves = np.concatenate([synth.synth_clip(i, L) for i, L in enumerate(Ls)])
+    prm = engine.make_params(l_harm=31, l_perc=31)
+    batch = engine.Batch(ctx, clip_lengths=Ls, n_fft=400, hop_length=160)
+    dev = engine.featuregram(batch, to_dev(waves), prm).cpu().numpy()
+    pinned = engine.host_alloc(waves.size)
+    pinned[:] = waves
+    host = engine.featuregram_host(batch, pinned, prm)
+    assert np.array_equal(dev, host)
+    host2 = engine.featuregram_host(batch, waves, prm)        # pageable memory also works
+    assert np.array_equal(dev, host2)
+
+
+def test_from_spec_dafx_variant(ctx):
+    rows, T = 201, 500
+    y = synth.synth_clip(3, 400 + 160 * (T - 1))
+    Spec = np.abs(lr.stft(y, n_fft=400, hop_length=160, win_length=400))
+    batch = engine.Batch(ctx, clip_frames=[T])
+    prm = engine.make_params(l_harm=21, l_perc=11, n_mels=120, feature="LOGMEL_HARMPERC")
+    got = engine.featuregram_from_spec(batch, to_dev(Spec.ravel()), rows, prm).cpu().numpy().reshape(240, T)
+    want = po.featuregram_from_spec(Spec, 21, 11, 120, "LogMelHarmPercSpec")
+    assert rel_l2(got, want) < REL_L2_TOL
+
+
+# ------------------------------------------------------------------------------ stats / patches
+def test_moments_and_stats_match_oracle(ctx):
+    D = 240
+    rng = np.random.default_rng(11)
+    Ts = [98, 40, 301, 77, 150, 64]
+    cls = [0, 1, 2, 0, 1, 2]
+    fvs = [(rng.standard_normal((D, T)) * 7 - 40).astype(np.float32) for T in Ts]
+    batch = engine.Batch(ctx, clip_frames=Ts)
+    acc = engine.moments(batch, to_dev(flat_batch(fvs)), D, cls, 3)
+    mean, std, counts, bad = engine.stats_finalize(acc.cpu().numpy(), D, 3)
+    names = ["music", "speech", "speech_music"]
+    groups = {n: [fvs[i] for i in range(len(Ts)) if cls[i] == k] for k, n in enumerate(names)}
+    want_mean, want_std, n0, n1, n2 = po.get_data_stats(groups, names)
+    assert bad == 0 and list(counts) == [n0, n1, n2]
+    assert np.allclose(mean, want_mean, rtol=1e-5, atol=1e-5)
+    assert np.allclose(std, want_std, rtol=1e-5, atol=1e-5)
+    # apply: Cython scale_data semantics (float64, eps 1e-10)
+    got = engine.scale_data(batch, to_dev(flat_batch(fvs)), D, to_dev(mean), to_dev(std)).cpu().numpy()
+    off = 0
+    for fv in fvs:
+        want = po.cscale_data(fv, mean, std)
+        assert np.allclose(got[off:off + fv.size].reshape(fv.shape), want, rtol=1e-12, atol=1e-12)
+        off += fv.size
+
+
+def test_row_standardize_and_patches(ctx):
+    D = 240
+    rng = np.random.default_rng(12)
+    Ts = [998, 300]
+    fvs = [(rng.standard_normal((D, T)) * 5 - 30).astype(np.float32) for T in Ts]
+    fvs[0][7] = 3.25                                         # constant row -> scale 1
+    batch = engine.Batch(ctx, clip_frames=Ts)
+    feat = to_dev(flat_batch(fvs))
+    engine.row_standardize(batch, feat, D)
+    for c, fv in enumerate(fvs):
+        want = po._standard_scale_rows(fv)
+        got = batch.clip(feat, D, c)
+        assert np.allclose(got.cpu().numpy(), want, rtol=0, atol=2e-6)
+        for (W, shift) in [(249, 24), (68, 68), (99, 1)]:
+            p = engine.extract_patches(ctx, got.contiguous(), W, shift).cpu().numpy()
+            wantp = po.extract_patches(got.cpu().numpy(), W, shift)
+            assert p.dtype == np.float64 and p.shape == wantp.shape
+            assert np.array_equal(p, wantp)
