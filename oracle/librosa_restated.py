@@ -99,6 +99,17 @@ def median_filter_1d(S: np.ndarray, k: int, axis: int) -> np.ndarray:
     return np.moveaxis(med, -1, axis)
 
 
+def scipy_median_well_defined(n: int, k: int) -> bool:
+    """scipy.ndimage's reflect handling returns index -1 (it reads the element *before* the
+    line, i.e. the previous row or out-of-bounds memory) once a window offset reaches a negative
+    multiple of 2n below -2n, i.e. when k//2 >= 4n.  Observed with scipy 1.18 on both the 1-D
+    fast path and the legacy N-D rank filter; the reference never gets there (shortest clip is
+    8 frames, lib/preprocessing.py:345-347; largest swept kernel 51).  Outside that regime scipy
+    and ``median_filter_1d`` agree bit for bit; inside it the oracle (and the CUDA kernel)
+    follow the mathematical definition."""
+    return n <= 1 or (k // 2) < 4 * n
+
+
 def median_filter_scipy(S: np.ndarray, k: int, axis: int) -> np.ndarray:
     """The routine librosa itself calls (fast path for the CPU baseline)."""
     from scipy.ndimage import median_filter

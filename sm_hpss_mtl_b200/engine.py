@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import weakref
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -229,25 +230,14 @@ def featuregram_from_spec(batch: Batch, S: torch.Tensor, rows: int, params: Para
 
 
 def host_alloc(n_floats: int) -> np.ndarray:
-    """float32 numpy array over pinned host memory owned by the library."""
+    """float32 numpy array over pinned host memory owned by the library (freed with the array)."""
     lib = _lib.load()
     p = C.c_void_p()
     check(lib.hpss_host_alloc(C.byref(p), int(n_floats) * 4))
     buf = (C.c_float * int(n_floats)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=np.float32)
-    arr._hpss_pinned = _Pinned(p)       # keeps the allocation alive with the array
+    weakref.finalize(arr, lib.hpss_host_free, C.c_void_p(p.value))    # views keep `arr` alive via .base
     return arr
-
-
-class _Pinned:
-    def __init__(self, p):
-        self.p = p
-
-    def __del__(self):
-        try:
-            _lib.load().hpss_host_free(self.p)
-        except Exception:
-            pass
 
 
 def featuregram_host(batch: Batch, wave_host: np.ndarray, params: Params, out_host: Optional[np.ndarray] = None):

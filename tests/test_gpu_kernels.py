@@ -18,8 +18,9 @@ REL_L2_TOL = 1e-4     # north_star: "librosa-matching features within 1e-4 relat
 
 
 def rel_l2(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a = np.asarray(a, dtype=dt)
+    b = np.asarray(b, dtype=dt)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
@@ -54,10 +55,13 @@ def test_median_bit_exact(ctx, rows, Ts, k):
     perc = engine.median_freq(batch, S, rows, k)
     torch.cuda.synchronize()
     for c, (h, p) in enumerate(zip(batch.split(harm, rows), batch.split(perc, rows))):
-        want_h = lr.median_filter_scipy(mats[c], k, axis=1)
-        want_p = lr.median_filter_scipy(mats[c], k, axis=0)
-        assert np.array_equal(h.cpu().numpy(), want_h), f"time-axis median differs (clip {c}, k={k})"
-        assert np.array_equal(p.cpu().numpy(), want_p), f"freq-axis median differs (clip {c}, k={k})"
+        assert np.array_equal(h.cpu().numpy(), lr.median_filter_1d(mats[c], k, axis=1)), f"time axis, clip {c}, k={k}"
+        assert np.array_equal(p.cpu().numpy(), lr.median_filter_1d(mats[c], k, axis=0)), f"freq axis, clip {c}, k={k}"
+        # scipy itself, wherever it is well defined (see test_oracle.py::test_scipy_reflect_overshoot_bug)
+        if lr.scipy_median_well_defined(Ts[c], k):
+            assert np.array_equal(h.cpu().numpy(), lr.median_filter_scipy(mats[c], k, axis=1))
+        if lr.scipy_median_well_defined(rows, k):
+            assert np.array_equal(p.cpu().numpy(), lr.median_filter_scipy(mats[c], k, axis=0))
 
 
 def test_median_all_fast_kernel_sizes(ctx):
