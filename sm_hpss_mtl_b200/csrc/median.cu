@@ -88,6 +88,20 @@ template <bool TIME_AXIS>
 __device__ __forceinline__ void tile_store(const float* __restrict__ sm, float* __restrict__ out, const LineInfo& li,
                                            int lane, int p0, int TT, int lstride) {
     if (TIME_AXIS) {
+        const int n0 = __shfl_sync(0xffffffffu, li.n, 0);
+        if (__all_sync(0xffffffffu, li.n == n0)) {
+            // uniform lengths: line r starts r*n0 elements after line 0
+            if (n0 == 0 || p0 >= n0) return;
+            float* row0 = out + __shfl_sync(0xffffffffu, li.base, 0) + p0;
+            const int lim = min(TT, n0 - p0);
+            for (int pos = lane; pos < lim; pos += 32) {
+                const float* s = sm + pos;
+                float* d = row0 + pos;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r, s += lstride, d += n0) *d = *s;
+            }
+            return;
+        }
         for (int r = 0; r < 32; ++r) {
             const int64_t b = __shfl_sync(0xffffffffu, li.base, r);
             const int n = __shfl_sync(0xffffffffu, li.n, r);
@@ -105,43 +119,166 @@ __device__ __forceinline__ void tile_store(const float* __restrict__ sm, float* 
 }
 
 // ---- fast path: odd k with a generated selection network ---------------------------
+// Persistent CTA = kComputeWarps compute warps + 1 loader warp around a ring of kRing... tile
+// buffers.  The loader warp fills tile n (cp.async, reflected at the clip borders) while the
+// compute warps run the selection networks on earlier tiles; full/empty mbarriers per buffer.
+// Item n of a CTA uses buffer n % NB and is consumed by compute warp n % kComputeWarps.
+constexpr int kComputeWarps = 8;
+constexpr int kLoaderWarps = 2;
+constexpr int kRingThreads = (kComputeWarps + kLoaderWarps) * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (count pre-armed)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// loader: fill one tile asynchronously
+// (loader warp `lw` of kLoaderWarps takes every kLoaderWarps-th row / position)
+template <bool TIME_AXIS>
+__device__ __forceinline__ void tile_fill_async(uint32_t sm_base, const float* __restrict__ S, const LineInfo& li,
+                                                int lane, int lw, int p0, int halo, int span, int lstride) {
+    if (TIME_AXIS) {
+        // lanes sweep positions of one row at a time (coalesced); reflected source indices are
+        // computed once per lane when all 32 rows have the same length (uniform batch)
+        const int n0 = __shfl_sync(0xffffffffu, li.n, 0);
+        const bool uniform = __all_sync(0xffffffffu, li.n == n0);
+        if (uniform) {
+            if (n0 == 0 || p0 >= n0) return;
+            // equal lengths => consecutive lines are exactly n0 elements apart, also across clips
+            const float* row0 = S + __shfl_sync(0xffffffffu, li.base, 0) + (int64_t)lw * n0;
+            const uint32_t dstep = 4u * (uint32_t)(kLoaderWarps * lstride);
+            const int sstep = kLoaderWarps * n0;
+            for (int pos = lane; pos < span; pos += 32) {
+                const float* src = row0 + reflect_idx(p0 - halo + pos, n0);
+                uint32_t d = sm_base + 4u * (uint32_t)(pos + lw * lstride);
+#pragma unroll 8
+                for (int r = lw; r < 32; r += kLoaderWarps, d += dstep, src += sstep) cp_async4(d, src);
+            }
+        } else {
+            for (int r = lw; r < 32; r += kLoaderWarps) {
+                const int64_t b = __shfl_sync(0xffffffffu, li.base, r);
+                const int n = __shfl_sync(0xffffffffu, li.n, r);
+                if (n == 0 || p0 >= n) continue;
+                for (int pos = lane; pos < span; pos += 32)
+                    cp_async4(sm_base + 4u * (uint32_t)(r * lstride + pos), S + b + reflect_idx(p0 - halo + pos, n));
+            }
+        }
+    } else {
+        if (li.n > 0) {
+            const float* col = S + li.base;
+            const int64_t es = li.estride;
+            // reflected head / tail, plain strided body (no index arithmetic per element)
+            const int first = p0 - halo;                       // source index of pos 0
+            const int body_lo = max(0, -first);                // first pos with an interior source
+            const int body_hi = min(span, li.n - first);       // one past the last interior pos
+            for (int pos = lw; pos < min(body_lo, span); pos += kLoaderWarps)
+                cp_async4(sm_base + 4u * (uint32_t)(pos * 32 + lane), col + reflect_idx(first + pos, li.n) * es);
+            {
+                int pos = body_lo + ((lw - body_lo) % kLoaderWarps + kLoaderWarps) % kLoaderWarps;
+                const float* src = col + (int64_t)(first + pos) * es;
+                uint32_t d = sm_base + 4u * (uint32_t)(pos * 32 + lane);
+                const int64_t sstep = es * kLoaderWarps;
+#pragma unroll 8
+                for (; pos < body_hi; pos += kLoaderWarps, src += sstep, d += 128u * kLoaderWarps) cp_async4(d, src);
+            }
+            {
+                int pos = max(body_hi, 0);
+                pos += ((lw - pos) % kLoaderWarps + kLoaderWarps) % kLoaderWarps;
+                for (; pos < span; pos += kLoaderWarps)
+                    cp_async4(sm_base + 4u * (uint32_t)(pos * 32 + lane), col + reflect_idx(first + pos, li.n) * es);
+            }
+        }
+    }
+}
+
 template <int K, bool TIME_AXIS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kRingThreads, 1)
 median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const int64_t* __restrict__ frame_off,
-                   int n_clips, int rows, int64_t n_lines, int TT, int n_ptiles, int64_t n_items) {
+                   int n_clips, int rows, int64_t n_lines, int TT, int n_ptiles, int64_t n_items, int NB) {
     constexpr int G = MedianGroup<K>::G;
     constexpr int HALO = K / 2;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int span = TT + K - 1;
     const int lstride = span | 1;
-    float* sm = smem + (size_t)warp * (TIME_AXIS ? 32 * lstride : span * 32);
+    const int tile_floats = TIME_AXIS ? 32 * lstride : span * 32;
     const int NG = TT / G;
-
-    for (int64_t item = (int64_t)blockIdx.x * kWarpsPerCta + warp; item < n_items;
-         item += (int64_t)gridDim.x * kWarpsPerCta) {
-        const int64_t lb = item / n_ptiles;
-        const int p0 = (int)(item - lb * n_ptiles) * TT;
-        const LineInfo li = lane_line<TIME_AXIS>(frame_off, n_clips, rows, n_lines, lb * 32 + lane);
-        // warp-uniform early exit: tile starts beyond every line of this warp
-        const bool live = li.n > 0 && p0 < li.n;
-        if (!__any_sync(0xffffffffu, live)) continue;
-        tile_load<TIME_AXIS>(sm, S, li, lane, p0, HALO, span, lstride);
-        __syncwarp();
-        if (live) {
-            const int ng = min(NG, (li.n - p0 + G - 1) / G);
-            for (int g = 0; g < ng; ++g) {
-                float x[K + G - 1], o[G];
-#pragma unroll
-                for (int i = 0; i < K + G - 1; ++i) x[i] = sm[sidx<TIME_AXIS>(lane, g * G + i, lstride)];
-                MedianGroup<K>::run(x, o);
-#pragma unroll
-                for (int j = 0; j < G; ++j) sm[sidx<TIME_AXIS>(lane, g * G + j, lstride)] = o[j];
-            }
+    // barriers live behind the tile ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NB * tile_floats);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NB);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NB; ++b) {
+            mbar_init(full0 + 8u * b, 32 * kLoaderWarps);   // every loader lane arrives once its cp.async land
+            mbar_init(empty0 + 8u * b, 1);     // one consumer lane releases the buffer
         }
-        __syncwarp();
-        tile_store<TIME_AXIS>(sm, out, li, lane, p0, TT, lstride);
-        __syncwarp();
+    }
+    __syncthreads();
+
+    const int64_t my_items = (n_items > blockIdx.x) ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp >= kComputeWarps) {
+        // ===== loader warps =====
+        const int lw = warp - kComputeWarps;
+        for (int64_t n = 0; n < my_items; ++n) {
+            const int b = (int)(n % NB);
+            const uint32_t use = (uint32_t)(n / NB);
+            if (use > 0) mbar_wait(empty0 + 8u * b, (use - 1) & 1u);
+            const int64_t item = blockIdx.x + n * gridDim.x;
+            const int64_t lb = item / n_ptiles;
+            const int p0 = (int)(item - lb * n_ptiles) * TT;
+            const LineInfo li = lane_line<TIME_AXIS>(frame_off, n_clips, rows, n_lines, lb * 32 + lane);
+            tile_fill_async<TIME_AXIS>(smem_u32(smem + (size_t)b * tile_floats), S, li, lane, lw, p0, HALO, span, lstride);
+            cp_async_arrive(full0 + 8u * b);
+        }
+    } else {
+        // ===== compute warps =====
+        for (int64_t n = warp; n < my_items; n += kComputeWarps) {
+            const int b = (int)(n % NB);
+            const uint32_t use = (uint32_t)(n / NB);
+            float* sm = smem + (size_t)b * tile_floats;
+            const int64_t item = blockIdx.x + n * gridDim.x;
+            const int64_t lb = item / n_ptiles;
+            const int p0 = (int)(item - lb * n_ptiles) * TT;
+            const LineInfo li = lane_line<TIME_AXIS>(frame_off, n_clips, rows, n_lines, lb * 32 + lane);
+            const bool live = li.n > 0 && p0 < li.n;
+            mbar_wait(full0 + 8u * b, use & 1u);
+            if (live) {
+                const int ng = min(NG, (li.n - p0 + G - 1) / G);
+                for (int g = 0; g < ng; ++g) {
+                    float x[K + G - 1], o[G];
+#pragma unroll
+                    for (int i = 0; i < K + G - 1; ++i) x[i] = sm[sidx<TIME_AXIS>(lane, g * G + i, lstride)];
+                    MedianGroup<K>::run(x, o);
+#pragma unroll
+                    for (int j = 0; j < G; ++j) sm[sidx<TIME_AXIS>(lane, g * G + j, lstride)] = o[j];
+                }
+            }
+            __syncwarp();
+            tile_store<TIME_AXIS>(sm, out, li, lane, p0, TT, lstride);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8u * b);
+        }
     }
 }
 
@@ -194,7 +331,16 @@ template <int K, bool TIME_AXIS>
 int launch_fast(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_frame_off, int n_clips, int rows,
                 int64_t n_lines, int64_t max_len, cudaStream_t st) {
     constexpr int G = MedianGroup<K>::G;
-    const int tt_max = 16 * G;
+    // largest tile (multiple of G outputs, at most 16 groups) that still leaves room for a ring of
+    // kComputeWarps + 2 buffers in the opt-in shared memory
+    const size_t per_buf = ((size_t)ctx->max_smem_optin - 512) / (kComputeWarps + 2) - 16;
+    const int max_span = (int)(per_buf / (32 * sizeof(float))) - 1;
+    int tt_max = (max_span - (K - 1)) / G * G;
+    if (tt_max > 16 * G) tt_max = 16 * G;
+    if (tt_max < G) {
+        set_error("median k=%d does not fit the shared-memory tile ring", K);
+        return HPSS_ERR_UNSUPPORTED;
+    }
     const int64_t nt0 = (max_len + tt_max - 1) / tt_max;
     int TT = (int)((max_len + nt0 - 1) / nt0);
     TT = (TT + G - 1) / G * G;
@@ -202,18 +348,16 @@ int launch_fast(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_fram
     const int64_t n_lb = (n_lines + 31) / 32;
     const int64_t n_items = n_lb * n_ptiles;
     const int span = TT + K - 1;
-    const size_t per_warp = (TIME_AXIS ? (size_t)32 * (span | 1) : (size_t)span * 32) * sizeof(float);
-    const size_t smem = per_warp * kWarpsPerCta;
+    const size_t tile_bytes = (TIME_AXIS ? (size_t)32 * (span | 1) : (size_t)span * 32) * sizeof(float);
+    int NB = (int)(((size_t)ctx->max_smem_optin - 512) / (tile_bytes + 16));
+    if (NB > 2 * kComputeWarps) NB = 2 * kComputeWarps;
+    const size_t smem = (size_t)NB * tile_bytes + (size_t)NB * 16;
     auto kern = median_fast_kernel<K, TIME_AXIS>;
     HPSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    HPSS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem));
-    if (occ < 1) occ = 1;
-    int64_t grid = (n_items + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int64_t cap = (int64_t)ctx->sm_count * occ;
-    if (grid > cap) grid = cap;
-    kern<<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(S, out, d_frame_off, n_clips, rows, n_lines, TT,
-                                                           n_ptiles, n_items);
+    int64_t grid = (n_items + kComputeWarps - 1) / kComputeWarps;
+    if (grid > ctx->sm_count) grid = ctx->sm_count;
+    kern<<<(unsigned)grid, kRingThreads, smem, st>>>(S, out, d_frame_off, n_clips, rows, n_lines, TT, n_ptiles,
+                                                     n_items, NB);
     HPSS_LAUNCHED("median_fast_kernel");
     return HPSS_OK;
 }
