@@ -216,7 +216,21 @@ static int make_batch(hpss_ctx* ctx, const std::vector<int64_t>& samples, const 
         b->frame_off[c + 1] = b->frame_off[c] + frames[c];
         b->max_frames = std::max(b->max_frames, frames[c]);
     }
+    // clip of the first frame of every 32-frame block (empty clips are skipped)
+    const int64_t total = b->frame_off[n];
+    std::vector<int32_t> block_clip((size_t)((total + 31) / 32) + 1, 0);
+    {
+        int c = 0;
+        for (size_t blk = 0; blk + 1 < block_clip.size() + 0; ++blk) {
+            const int64_t g = (int64_t)blk * 32;
+            while (c < n && b->frame_off[c + 1] <= g) ++c;
+            block_clip[blk] = c < n ? c : (n > 0 ? n - 1 : 0);
+        }
+    }
     cudaError_t e = cudaMalloc(&b->d_frame_off, sizeof(int64_t) * (n + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_block_clip, sizeof(int32_t) * block_clip.size());
+    if (e == cudaSuccess)
+        e = cudaMemcpy(b->d_block_clip, block_clip.data(), sizeof(int32_t) * block_clip.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_sample_off, sizeof(int64_t) * (n + 1));
     if (e == cudaSuccess)
         e = cudaMemcpy(b->d_frame_off, b->frame_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice);
@@ -225,6 +239,7 @@ static int make_batch(hpss_ctx* ctx, const std::vector<int64_t>& samples, const 
     if (e != cudaSuccess) {
         if (b->d_frame_off) cudaFree(b->d_frame_off);
         if (b->d_sample_off) cudaFree(b->d_sample_off);
+        if (b->d_block_clip) cudaFree(b->d_block_clip);
         delete b;
         return cuda_fail(e, "batch offsets");
     }
@@ -440,6 +455,7 @@ int hpss_batch_destroy(hpss_batch* b) {
     cudaDeviceSynchronize();
     if (b->d_frame_off) cudaFree(b->d_frame_off);
     if (b->d_sample_off) cudaFree(b->d_sample_off);
+    if (b->d_block_clip) cudaFree(b->d_block_clip);
     if (b->d_stft_tiles) cudaFree(b->d_stft_tiles);
     if (b->d_clip_class) cudaFree(b->d_clip_class);
     for (auto* s : b->host_chunks) hpss_batch_destroy(s);

@@ -81,6 +81,7 @@ struct hpss_batch {
     int64_t max_frames = 0;
     int64_t* d_sample_off = nullptr;
     int64_t* d_frame_off = nullptr;
+    int32_t* d_block_clip = nullptr;   // clip of the first frame of every 32-frame block of the batch
     // K1 tile list (clip, first frame), built for a given tile height
     int stft_tt = 0;
     int n_stft_tiles = 0;
@@ -144,6 +145,15 @@ __device__ __forceinline__ int find_clip(const int64_t* __restrict__ off, int n,
         if (__ldg(off + mid) <= g) lo = mid; else hi = mid;
     }
     return lo;
+}
+
+// clip of global frame g, starting from the clip of its 32-frame block (block_clip[g / 32]):
+// a short forward walk instead of a binary search through global memory
+__device__ __forceinline__ int find_clip_hint(const int64_t* __restrict__ off, const int32_t* __restrict__ block_clip,
+                                              int64_t g) {
+    int c = __ldg(block_clip + (g >> 5));
+    while (__ldg(off + c + 1) <= g) ++c;
+    return c;
 }
 
 // order-preserving float <-> uint mapping for atomicMax on floats of either sign

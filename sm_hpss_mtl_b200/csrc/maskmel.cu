@@ -24,7 +24,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kFC = 64;   // frequency rows staged per chunk
+constexpr int kFCsplit = 64;    // frequency rows staged per chunk when a whole column does not fit
+constexpr int kFCwhole = 264;   // up to this many rows the whole column is staged at once
 
 struct FrameLane {
     bool valid;
@@ -34,13 +35,13 @@ struct FrameLane {
     int64_t out_base;   // + row*T
 };
 
-__device__ __forceinline__ FrameLane frame_lane(const int64_t* __restrict__ frame_off, int n_clips, int64_t total,
+__device__ __forceinline__ FrameLane frame_lane(const int64_t* __restrict__ frame_off, const int32_t* __restrict__ block_clip, int64_t total,
                                                 int64_t gf, int rows_in, int rows_out) {
     FrameLane fl;
     fl.valid = gf < total;
     fl.clip = 0; fl.T = 1; fl.in_base = 0; fl.out_base = 0;
     if (fl.valid) {
-        const int c = find_clip(frame_off, n_clips, gf);
+        const int c = find_clip_hint(frame_off, block_clip, gf);
         const int64_t fo = __ldg(frame_off + c);
         fl.clip = c;
         fl.T = (int)(__ldg(frame_off + c + 1) - fo);
@@ -69,7 +70,7 @@ __device__ __forceinline__ void softmask_apply(float s, float h, float p, float&
 __device__ __forceinline__ float post_value(float x, int log_power, float amin) {
     if (!log_power) return x;
     const float x2 = __fmul_rn(x, x);
-    return 10.0f * log10f(fmaxf(amin, x2));
+    return 3.0102999566398120f * __log2f(fmaxf(amin, x2));   // 10*log10(x), MUFU.LG2: |err| ~ 1e-6 dB
 }
 
 // per-(clip, stream) running max -> global ordered-uint atomicMax, one atomic per
@@ -86,20 +87,20 @@ __device__ __forceinline__ void publish_max(uint32_t* __restrict__ clip_max, int
 template <bool HPSS_MODE>
 __global__ void __launch_bounds__(kThreads)
 mask_mel_kernel(const float* __restrict__ S, const float* __restrict__ harm, const float* __restrict__ perc,
-                const int64_t* __restrict__ frame_off, int n_clips, int64_t total_frames, int rows,
+                const int64_t* __restrict__ frame_off, const int32_t* __restrict__ block_clip, int64_t total_frames, int rows,
                 const float* __restrict__ mel, const int2* __restrict__ band, int n_mels, int pre_square,
-                int log_power, float amin, float* __restrict__ out, uint32_t* __restrict__ clip_max) {
+                int log_power, float amin, float* __restrict__ out, uint32_t* __restrict__ clip_max, int FC) {
     constexpr int NS = HPSS_MODE ? 2 : 1;
     extern __shared__ float smem[];
     __shared__ float s_max[NS][kWarps][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool project = mel != nullptr;
     const int rows_out = NS * (project ? n_mels : rows);
-    const FrameLane fl = frame_lane(frame_off, n_clips, total_frames, (int64_t)blockIdx.x * 32 + lane, rows, rows_out);
+    const FrameLane fl = frame_lane(frame_off, block_clip, total_frames, (int64_t)blockIdx.x * 32 + lane, rows, rows_out);
 
     float vmax[NS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) vmax[s] = -INFINITY;
+    for (int s = 0; s < NS; ++s) vmax[s] = -INFINITY;   // only constant indices below (stays in registers)
 
     if (!project) {
         // identity projection: [H; P] (or plain S) rows, optional power_to_db
@@ -123,14 +124,11 @@ mask_mel_kernel(const float* __restrict__ S, const float* __restrict__ harm, con
             }
         }
     } else {
-        float* Hc = smem;                       // [kFC][32]
-        float* Pc = Hc + kFC * 32;              // [kFC][32]   (HPSS mode only)
-        float* acc = HPSS_MODE ? Pc + kFC * 32 : Pc;   // [NS][n_mels][32]
-        for (int i = threadIdx.x; i < NS * n_mels * 32; i += kThreads) acc[i] = 0.f;
-        for (int f0 = 0; f0 < rows; f0 += kFC) {
-            const int fe = min(rows, f0 + kFC);
-            // phase 1: masked values of this chunk -> shared memory
-            for (int f = f0 + warp; f < fe; f += kWarps) {
+        float* Hc = smem;                       // [FC][32]
+        float* Pc = Hc + FC * 32;               // [FC][32]   (HPSS mode only)
+        if (FC >= rows) {
+            // whole column staged at once: mask phase, then every filter accumulates in registers
+            for (int f = warp; f < rows; f += kWarps) {
                 float H = 0.f, P = 0.f;
                 if (fl.valid) {
                     const int64_t gi = fl.in_base + (int64_t)f * fl.T;
@@ -138,33 +136,72 @@ mask_mel_kernel(const float* __restrict__ S, const float* __restrict__ harm, con
                     if (HPSS_MODE) softmask_apply(sv, __ldg(harm + gi), __ldg(perc + gi), H, P);
                     else H = pre_square ? __fmul_rn(sv, sv) : sv;
                 }
-                Hc[(f - f0) * 32 + lane] = H;
-                if (HPSS_MODE) Pc[(f - f0) * 32 + lane] = P;
+                Hc[f * 32 + lane] = H;
+                if (HPSS_MODE) Pc[f * 32 + lane] = P;
             }
             __syncthreads();
-            // phase 2: banded projection of the chunk
             for (int m = warp; m < n_mels; m += kWarps) {
                 const int2 bd = __ldg(band + m);
-                const int a = max(bd.x, f0), b = min(bd.y, fe);
-                if (a >= b) continue;
                 float sh = 0.f, sp = 0.f;
                 const float* w = mel + (size_t)m * rows;
-                for (int f = a; f < b; ++f) {
+                for (int f = bd.x; f < bd.y; ++f) {
                     const float wf = __ldg(w + f);
-                    sh = fmaf(wf, Hc[(f - f0) * 32 + lane], sh);
-                    if (HPSS_MODE) sp = fmaf(wf, Pc[(f - f0) * 32 + lane], sp);
+                    sh = fmaf(wf, Hc[f * 32 + lane], sh);
+                    if (HPSS_MODE) sp = fmaf(wf, Pc[f * 32 + lane], sp);
                 }
-                acc[m * 32 + lane] += sh;
-                if (HPSS_MODE) acc[(n_mels + m) * 32 + lane] += sp;
+                if (fl.valid) {
+                    const float a = post_value(sh, log_power, amin);
+                    out[fl.out_base + (int64_t)m * fl.T] = a;
+                    vmax[0] = fmaxf(vmax[0], a);
+                    if (HPSS_MODE) {
+                        const float b = post_value(sp, log_power, amin);
+                        out[fl.out_base + (int64_t)(n_mels + m) * fl.T] = b;
+                        vmax[NS - 1] = fmaxf(vmax[NS - 1], b);
+                    }
+                }
             }
-            __syncthreads();
-        }
-        for (int r = warp; r < NS * n_mels; r += kWarps) {
-            if (!fl.valid) continue;
-            const float a = post_value(acc[r * 32 + lane], log_power, amin);
-            out[fl.out_base + (int64_t)r * fl.T] = a;
-            const int s = (NS == 2 && r >= n_mels) ? 1 : 0;
-            vmax[s] = fmaxf(vmax[s], a);
+        } else {
+            float* acc = HPSS_MODE ? Pc + FC * 32 : Pc;   // [NS][n_mels][32]
+            for (int i = threadIdx.x; i < NS * n_mels * 32; i += kThreads) acc[i] = 0.f;
+            for (int f0 = 0; f0 < rows; f0 += FC) {
+                const int fe = min(rows, f0 + FC);
+                // phase 1: masked values of this chunk -> shared memory
+                for (int f = f0 + warp; f < fe; f += kWarps) {
+                    float H = 0.f, P = 0.f;
+                    if (fl.valid) {
+                        const int64_t gi = fl.in_base + (int64_t)f * fl.T;
+                        const float sv = __ldg(S + gi);
+                        if (HPSS_MODE) softmask_apply(sv, __ldg(harm + gi), __ldg(perc + gi), H, P);
+                        else H = pre_square ? __fmul_rn(sv, sv) : sv;
+                    }
+                    Hc[(f - f0) * 32 + lane] = H;
+                    if (HPSS_MODE) Pc[(f - f0) * 32 + lane] = P;
+                }
+                __syncthreads();
+                // phase 2: banded projection of the chunk
+                for (int m = warp; m < n_mels; m += kWarps) {
+                    const int2 bd = __ldg(band + m);
+                    const int a = max(bd.x, f0), b = min(bd.y, fe);
+                    if (a >= b) continue;
+                    float sh = 0.f, sp = 0.f;
+                    const float* w = mel + (size_t)m * rows;
+                    for (int f = a; f < b; ++f) {
+                        const float wf = __ldg(w + f);
+                        sh = fmaf(wf, Hc[(f - f0) * 32 + lane], sh);
+                        if (HPSS_MODE) sp = fmaf(wf, Pc[(f - f0) * 32 + lane], sp);
+                    }
+                    acc[m * 32 + lane] += sh;
+                    if (HPSS_MODE) acc[(n_mels + m) * 32 + lane] += sp;
+                }
+                __syncthreads();
+            }
+            for (int r = warp; r < NS * n_mels; r += kWarps) {
+                if (!fl.valid) continue;
+                const float a = post_value(acc[r * 32 + lane], log_power, amin);
+                out[fl.out_base + (int64_t)r * fl.T] = a;
+                if (NS == 2 && r >= n_mels) vmax[NS - 1] = fmaxf(vmax[NS - 1], a);
+                else vmax[0] = fmaxf(vmax[0], a);
+            }
         }
     }
 
@@ -182,11 +219,11 @@ mask_mel_kernel(const float* __restrict__ S, const float* __restrict__ harm, con
 }
 
 __global__ void __launch_bounds__(kThreads)
-topdb_kernel(float* __restrict__ out, const int64_t* __restrict__ frame_off, int n_clips, int64_t total_frames,
+topdb_kernel(float* __restrict__ out, const int64_t* __restrict__ frame_off, const int32_t* __restrict__ block_clip, int64_t total_frames,
              int rows_per_stream, int n_streams, const uint32_t* __restrict__ clip_max, float top_db) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows = rows_per_stream * n_streams;
-    const FrameLane fl = frame_lane(frame_off, n_clips, total_frames, (int64_t)blockIdx.x * 32 + lane, rows, rows);
+    const FrameLane fl = frame_lane(frame_off, block_clip, total_frames, (int64_t)blockIdx.x * 32 + lane, rows, rows);
     if (!fl.valid) return;
     for (int s = 0; s < n_streams; ++s) {
         const float thr = ordered_to_float(__ldg(clip_max + (size_t)n_streams * fl.clip + s)) - top_db;
@@ -228,7 +265,11 @@ int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const fl
     if (clip_max) HPSS_CUDA(cudaMemsetAsync(clip_max, 0, sizeof(uint32_t) * (size_t)ns * b->n_clips, st));
     if (total == 0) return HPSS_OK;
     size_t smem = 0;
-    if (mel) smem = ((size_t)ns * kFC * 32 + (size_t)ns * n_mels * 32) * sizeof(float);
+    int FC = 0;
+    if (mel) {
+        if (rows <= kFCwhole) { FC = rows; smem = (size_t)ns * FC * 32 * sizeof(float); }
+        else { FC = kFCsplit; smem = ((size_t)ns * FC * 32 + (size_t)ns * n_mels * 32) * sizeof(float); }
+    }
     if (smem > (size_t)ctx->max_smem_optin) {
         set_error("n_mels=%d needs %zu bytes of shared memory (max %d)", n_mels, smem, ctx->max_smem_optin);
         return HPSS_ERR_UNSUPPORTED;
@@ -236,14 +277,14 @@ int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const fl
     const unsigned grid = (unsigned)((total + 31) / 32);
     if (hpss_mode) {
         HPSS_CUDA(cudaFuncSetAttribute(mask_mel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mask_mel_kernel<true><<<grid, kThreads, smem, st>>>(S, harm, perc, b->d_frame_off, b->n_clips, total, rows,
+        mask_mel_kernel<true><<<grid, kThreads, smem, st>>>(S, harm, perc, b->d_frame_off, b->d_block_clip, total, rows,
                                                             mel, band, n_mels, pre_square, log_power, amin, out,
-                                                            clip_max);
+                                                            clip_max, FC);
     } else {
         HPSS_CUDA(cudaFuncSetAttribute(mask_mel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mask_mel_kernel<false><<<grid, kThreads, smem, st>>>(S, nullptr, nullptr, b->d_frame_off, b->n_clips, total,
+        mask_mel_kernel<false><<<grid, kThreads, smem, st>>>(S, nullptr, nullptr, b->d_frame_off, b->d_block_clip, total,
                                                              rows, mel, band, n_mels, pre_square, log_power, amin,
-                                                             out, clip_max);
+                                                             out, clip_max, FC);
     }
     HPSS_LAUNCHED("mask_mel_kernel");
     return HPSS_OK;
@@ -255,7 +296,7 @@ int launch_topdb(hpss_ctx* ctx, const hpss_batch* b, float* out, int rows_per_st
     const int64_t total = b->frame_off[b->n_clips];
     if (total == 0) return HPSS_OK;
     const unsigned grid = (unsigned)((total + 31) / 32);
-    topdb_kernel<<<grid, kThreads, 0, st>>>(out, b->d_frame_off, b->n_clips, total, rows_per_stream, n_streams,
+    topdb_kernel<<<grid, kThreads, 0, st>>>(out, b->d_frame_off, b->d_block_clip, total, rows_per_stream, n_streams,
                                             clip_max, top_db);
     HPSS_LAUNCHED("topdb_kernel");
     return HPSS_OK;

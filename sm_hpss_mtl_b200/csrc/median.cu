@@ -30,8 +30,9 @@ struct LineInfo {
 };
 
 template <bool TIME_AXIS>
-__device__ __forceinline__ LineInfo lane_line(const int64_t* __restrict__ frame_off, int n_clips, int rows,
-                                              int64_t n_lines, int64_t line) {
+__device__ __forceinline__ LineInfo lane_line(const int64_t* __restrict__ frame_off,
+                                              const int32_t* __restrict__ block_clip, int rows, int64_t n_lines,
+                                              int64_t line) {
     LineInfo li;
     li.base = 0; li.n = 0; li.estride = 1;
     if (line >= n_lines) return li;
@@ -44,7 +45,7 @@ __device__ __forceinline__ LineInfo lane_line(const int64_t* __restrict__ frame_
         li.n = T;
         li.estride = 1;
     } else {
-        const int c = find_clip(frame_off, n_clips, line);
+        const int c = find_clip_hint(frame_off, block_clip, line);
         const int64_t fo = __ldg(frame_off + c);
         const int T = (int)(__ldg(frame_off + c + 1) - fo);
         li.base = (int64_t)rows * fo + (line - fo);
@@ -215,7 +216,8 @@ __device__ __forceinline__ void tile_fill_async(uint32_t sm_base, const float* _
 template <int K, bool TIME_AXIS>
 __global__ void __launch_bounds__(kRingThreads, 1)
 median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const int64_t* __restrict__ frame_off,
-                   int n_clips, int rows, int64_t n_lines, int TT, int n_ptiles, int64_t n_items, int NB) {
+                   const int32_t* __restrict__ block_clip, int rows, int64_t n_lines, int TT, int n_ptiles,
+                   int64_t n_items, int NB) {
     constexpr int G = MedianGroup<K>::G;
     constexpr int HALO = K / 2;
     extern __shared__ __align__(16) float smem[];
@@ -247,7 +249,7 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
             const int64_t item = blockIdx.x + n * gridDim.x;
             const int64_t lb = item / n_ptiles;
             const int p0 = (int)(item - lb * n_ptiles) * TT;
-            const LineInfo li = lane_line<TIME_AXIS>(frame_off, n_clips, rows, n_lines, lb * 32 + lane);
+            const LineInfo li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane);
             tile_fill_async<TIME_AXIS>(smem_u32(smem + (size_t)b * tile_floats), S, li, lane, lw, p0, HALO, span, lstride);
             cp_async_arrive(full0 + 8u * b);
         }
@@ -260,7 +262,7 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
             const int64_t item = blockIdx.x + n * gridDim.x;
             const int64_t lb = item / n_ptiles;
             const int p0 = (int)(item - lb * n_ptiles) * TT;
-            const LineInfo li = lane_line<TIME_AXIS>(frame_off, n_clips, rows, n_lines, lb * 32 + lane);
+            const LineInfo li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane);
             const bool live = li.n > 0 && p0 < li.n;
             mbar_wait(full0 + 8u * b, use & 1u);
             if (live) {
@@ -286,7 +288,8 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
 template <bool TIME_AXIS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 median_generic_kernel(const float* __restrict__ S, float* __restrict__ out, const int64_t* __restrict__ frame_off,
-                      int n_clips, int rows, int64_t n_lines, int k, int TT, int n_ptiles, int64_t n_items) {
+                      const int32_t* __restrict__ block_clip, int rows, int64_t n_lines, int k, int TT, int n_ptiles,
+                      int64_t n_items) {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = k / 2, rank = k / 2;
@@ -298,7 +301,7 @@ median_generic_kernel(const float* __restrict__ S, float* __restrict__ out, cons
          item += (int64_t)gridDim.x * kWarpsPerCta) {
         const int64_t lb = item / n_ptiles;
         const int p0 = (int)(item - lb * n_ptiles) * TT;
-        const LineInfo li = lane_line<TIME_AXIS>(frame_off, n_clips, rows, n_lines, lb * 32 + lane);
+        const LineInfo li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane);
         const bool live = li.n > 0 && p0 < li.n;
         if (!__any_sync(0xffffffffu, live)) continue;
         tile_load<TIME_AXIS>(sm, S, li, lane, p0, halo, span, lstride);
@@ -328,7 +331,7 @@ median_generic_kernel(const float* __restrict__ S, float* __restrict__ out, cons
 }
 
 template <int K, bool TIME_AXIS>
-int launch_fast(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_frame_off, int n_clips, int rows,
+int launch_fast(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_frame_off, const int32_t* d_block_clip, int rows,
                 int64_t n_lines, int64_t max_len, cudaStream_t st) {
     constexpr int G = MedianGroup<K>::G;
     // largest tile (multiple of G outputs, at most 16 groups) that still leaves room for a ring of
@@ -356,14 +359,14 @@ int launch_fast(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_fram
     HPSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = (n_items + kComputeWarps - 1) / kComputeWarps;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
-    kern<<<(unsigned)grid, kRingThreads, smem, st>>>(S, out, d_frame_off, n_clips, rows, n_lines, TT, n_ptiles,
+    kern<<<(unsigned)grid, kRingThreads, smem, st>>>(S, out, d_frame_off, d_block_clip, rows, n_lines, TT, n_ptiles,
                                                      n_items, NB);
     HPSS_LAUNCHED("median_fast_kernel");
     return HPSS_OK;
 }
 
 template <bool TIME_AXIS>
-int launch_generic(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_frame_off, int n_clips, int rows,
+int launch_generic(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_frame_off, const int32_t* d_block_clip, int rows,
                    int64_t n_lines, int64_t max_len, int k, cudaStream_t st) {
     // per-warp tile of at most ~40 KB of shared memory
     int tt_max = 320 - k;
@@ -388,7 +391,7 @@ int launch_generic(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_f
     int64_t grid = (n_items + kWarpsPerCta - 1) / kWarpsPerCta;
     const int64_t cap = (int64_t)ctx->sm_count * occ;
     if (grid > cap) grid = cap;
-    kern<<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(S, out, d_frame_off, n_clips, rows, n_lines, k, TT,
+    kern<<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(S, out, d_frame_off, d_block_clip, rows, n_lines, k, TT,
                                                            n_ptiles, n_items);
     HPSS_LAUNCHED("median_generic_kernel");
     return HPSS_OK;
@@ -412,15 +415,15 @@ int launch_median(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, 
     }
 #define HPSS_DISPATCH_K(KK)                                                                                   \
     if (k == KK) {                                                                                            \
-        return time_axis ? launch_fast<KK, true>(ctx, S, out, b->d_frame_off, b->n_clips, rows, n_lines,      \
+        return time_axis ? launch_fast<KK, true>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines,      \
                                                  max_len, st)                                                 \
-                         : launch_fast<KK, false>(ctx, S, out, b->d_frame_off, b->n_clips, rows, n_lines,     \
+                         : launch_fast<KK, false>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines,     \
                                                   max_len, st);                                               \
     }
     HPSS_MEDIAN_FAST_KS(HPSS_DISPATCH_K)
 #undef HPSS_DISPATCH_K
-    return time_axis ? launch_generic<true>(ctx, S, out, b->d_frame_off, b->n_clips, rows, n_lines, max_len, k, st)
-                     : launch_generic<false>(ctx, S, out, b->d_frame_off, b->n_clips, rows, n_lines, max_len, k, st);
+    return time_axis ? launch_generic<true>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines, max_len, k, st)
+                     : launch_generic<false>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines, max_len, k, st);
 }
 
 }  // namespace hpss

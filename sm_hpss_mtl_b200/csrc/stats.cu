@@ -19,82 +19,80 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Raw moments.  Persistent CTAs walk tiles of 32 frames; per (row, tile) a warp reduces its
-// 32 lanes in float64 and adds into CTA-private shared accumulators; one float64 atomicAdd
-// per accumulator and CTA at the end.
+// Raw moments.  grid = (frame chunks, groups of 8 feature rows): every warp owns ONE feature row
+// for its whole life and walks the clips of its frame chunk (lanes along time, coalesced 128-byte
+// reads); per-lane float64 accumulators (one sum per class + the sum of squares) stay in
+// registers and are reduced across the warp once, at the end: 1 + n_classes float64 atomics per warp.
+template <int MAXC>
 __global__ void __launch_bounds__(kThreads)
-moments_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_off, int n_clips,
-               int64_t total_frames, int D, const int32_t* __restrict__ clip_class, int n_classes,
-               double* __restrict__ g_sum, double* __restrict__ g_sumsq, double* __restrict__ g_count,
-               double* __restrict__ g_nonfinite) {
-    extern __shared__ double sacc[];   // [n_classes][D] sums, then [D] sumsq
-    double* s_sum = sacc;
-    double* s_sq = sacc + (size_t)n_classes * D;
-    __shared__ unsigned long long s_bad;
+moments_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_off,
+               const int32_t* __restrict__ block_clip, int n_clips, int64_t total_frames, int64_t chunk_frames,
+               int D, const int32_t* __restrict__ clip_class, int n_classes, double* __restrict__ g_sum,
+               double* __restrict__ g_sumsq, double* __restrict__ g_count, double* __restrict__ g_nonfinite) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < (n_classes + 1) * D; i += kThreads) sacc[i] = 0.0;
-    if (threadIdx.x == 0) s_bad = 0ull;
-    __syncthreads();
-
-    unsigned long long bad = 0;
-    const int64_t n_tiles = (total_frames + 31) / 32;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t gf = tile * 32 + lane;
-        const bool valid = gf < total_frames;
-        int cls = -1, T = 1;
-        int64_t base = 0;
-        if (valid) {
-            const int c = find_clip(frame_off, n_clips, gf);
-            const int64_t fo = __ldg(frame_off + c);
-            T = (int)(__ldg(frame_off + c + 1) - fo);
-            base = (int64_t)D * fo + (gf - fo);
-            cls = __ldg(clip_class + c);
-        }
-        const int cls0 = __shfl_sync(0xffffffffu, cls, 0);
-        const bool uniform = __all_sync(0xffffffffu, cls == cls0 || !valid);
-        for (int d = warp; d < D; d += kWarps) {
-            float x = 0.f;
-            if (valid) {
-                x = __ldg(feat + base + (int64_t)d * T);
+    const int d = blockIdx.y * kWarps + warp;
+    if (d < D) {
+        double s[MAXC];
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) s[k] = 0.0;
+        double q = 0.0;
+        unsigned bad = 0;
+        int64_t g0 = (int64_t)blockIdx.x * chunk_frames;
+        const int64_t g1 = min(total_frames, g0 + chunk_frames);
+        int c = find_clip_hint(frame_off, block_clip, g0);
+        while (g0 < g1) {
+            const int64_t fo = __ldg(frame_off + c), fe = __ldg(frame_off + c + 1);
+            const int64_t seg_end = min(g1, fe);
+            const int T = (int)(fe - fo), len = (int)(seg_end - g0);
+            const int cls = __ldg(clip_class + c);
+            const float* row = feat + (int64_t)D * fo + (int64_t)d * T + (g0 - fo);
+            double ps = 0.0;
+            for (int t = lane; t < len; t += 32) {
+                float x = __ldg(row + t);
                 if (!isfinite(x)) { x = 0.f; ++bad; }
+                const double xd = (double)x;
+                ps += xd;
+                q = fma(xd, xd, q);
             }
-            const double xd = (double)x;
-            const double sq = warp_sum(xd * xd);
-            if (uniform) {
-                const double s = warp_sum(xd);
-                if (lane == 0) { s_sum[(size_t)cls0 * D + d] += s; s_sq[d] += sq; }
-            } else {
-                for (int k = 0; k < n_classes; ++k) {
-                    const double s = warp_sum(cls == k ? xd : 0.0);
-                    if (lane == 0) s_sum[(size_t)k * D + d] += s;
-                }
-                if (lane == 0) s_sq[d] += sq;
+#pragma unroll
+            for (int k = 0; k < MAXC; ++k) s[k] += (k == cls) ? ps : 0.0;
+            g0 = seg_end;
+            ++c;
+            while (g0 < g1 && __ldg(frame_off + c + 1) <= g0) ++c;   // skip empty clips
+        }
+        q = warp_sum(q);
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            if (k < n_classes) {
+                const double t = warp_sum(s[k]);
+                if (lane == 0 && t != 0.0) atomicAdd(g_sum + (size_t)k * D + d, t);
             }
+        }
+        bad = __reduce_add_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            if (q != 0.0) atomicAdd(g_sumsq + d, q);
+            if (bad) atomicAdd(g_nonfinite, (double)bad);
         }
     }
-    if (bad) atomicAdd(&s_bad, bad);
-    __syncthreads();
-    for (int i = threadIdx.x; i < n_classes * D; i += kThreads)
-        if (s_sum[i] != 0.0) atomicAdd(g_sum + i, s_sum[i]);
-    for (int i = threadIdx.x; i < D; i += kThreads)
-        if (s_sq[i] != 0.0) atomicAdd(g_sumsq + i, s_sq[i]);
-    if (threadIdx.x == 0 && s_bad) atomicAdd(g_nonfinite, (double)s_bad);
-    // frame counts per class (clip granularity)
-    for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < n_clips; c += (int64_t)gridDim.x * kThreads) {
-        const double T = (double)(frame_off[c + 1] - frame_off[c]);
-        atomicAdd(g_count + clip_class[c], T);
+    // frame counts per class (clip granularity), once
+    if (blockIdx.y == 0) {
+        for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < n_clips; c += (int64_t)gridDim.x * kThreads) {
+            const double T = (double)(frame_off[c + 1] - frame_off[c]);
+            if (T > 0) atomicAdd(g_count + clip_class[c], T);
+        }
     }
 }
 
 // (x - mean) / (stdev + eps) in float64, lane = frame
 __global__ void __launch_bounds__(kThreads)
-scale_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_off, int n_clips, int64_t total_frames,
+scale_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_off,
+             const int32_t* __restrict__ block_clip, int64_t total_frames,
              int D, const float* __restrict__ mean, const float* __restrict__ stdev, double eps,
              double* __restrict__ out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t gf = (int64_t)blockIdx.x * 32 + lane;
     if (gf >= total_frames) return;
-    const int c = find_clip(frame_off, n_clips, gf);
+    const int c = find_clip_hint(frame_off, block_clip, gf);
     const int64_t fo = __ldg(frame_off + c);
     const int T = (int)(__ldg(frame_off + c + 1) - fo);
     const int64_t base = (int64_t)D * fo + (gf - fo);
@@ -162,17 +160,24 @@ int launch_moments(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D,
                    int n_classes, double* sum, double* sumsq, double* count, double* nonfinite, cudaStream_t st) {
     const int64_t total = b->frame_off[b->n_clips];
     if (total == 0) return HPSS_OK;
-    const size_t smem = (size_t)(n_classes + 1) * D * sizeof(double);
-    if (smem > (size_t)ctx->max_smem_optin) {
-        set_error("moments: D=%d x classes=%d does not fit shared memory", D, n_classes);
+    if (n_classes > 8) {
+        set_error("moments: at most 8 classes are supported (got %d)", n_classes);
         return HPSS_ERR_UNSUPPORTED;
     }
-    HPSS_CUDA(cudaFuncSetAttribute(moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t n_tiles = (total + 31) / 32;
-    int64_t grid = (int64_t)ctx->sm_count * 4;
-    if (grid > n_tiles) grid = n_tiles;
-    moments_kernel<<<(unsigned)grid, kThreads, smem, st>>>(feat, b->d_frame_off, b->n_clips, total, D, d_class,
-                                                           n_classes, sum, sumsq, count, nonfinite);
+    // frame chunks: multiples of 32 frames, enough CTAs for ~8 waves of 8 resident CTAs per SM
+    const int row_groups = (D + kWarps - 1) / kWarps;
+    int64_t want_chunks = ((int64_t)ctx->sm_count * 64 + row_groups - 1) / row_groups;
+    int64_t chunk = (total + want_chunks - 1) / want_chunks;
+    chunk = (chunk + 31) / 32 * 32;
+    if (chunk < 1024) chunk = 1024;
+    const int64_t n_chunks = (total + chunk - 1) / chunk;
+    dim3 grid((unsigned)n_chunks, (unsigned)row_groups);
+    if (n_classes <= 4)
+        moments_kernel<4><<<grid, kThreads, 0, st>>>(feat, b->d_frame_off, b->d_block_clip, b->n_clips, total, chunk, D,
+                                                     d_class, n_classes, sum, sumsq, count, nonfinite);
+    else
+        moments_kernel<8><<<grid, kThreads, 0, st>>>(feat, b->d_frame_off, b->d_block_clip, b->n_clips, total, chunk, D,
+                                                     d_class, n_classes, sum, sumsq, count, nonfinite);
     HPSS_LAUNCHED("moments_kernel");
     return HPSS_OK;
 }
@@ -182,7 +187,7 @@ int launch_scale(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, c
     (void)ctx;
     const int64_t total = b->frame_off[b->n_clips];
     if (total == 0) return HPSS_OK;
-    scale_kernel<<<(unsigned)((total + 31) / 32), kThreads, 0, st>>>(feat, b->d_frame_off, b->n_clips, total, D, mean,
+    scale_kernel<<<(unsigned)((total + 31) / 32), kThreads, 0, st>>>(feat, b->d_frame_off, b->d_block_clip, total, D, mean,
                                                                      stdev, eps, out);
     HPSS_LAUNCHED("scale_kernel");
     return HPSS_OK;

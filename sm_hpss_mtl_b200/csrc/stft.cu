@@ -12,9 +12,20 @@ namespace hpss {
 
 namespace {
 
+// division by a launch-invariant small divisor: q = umulhi(x, ceil(2^32 / d)), exact while x*d < 2^32
+struct FastDiv {
+    uint32_t magic, d;
+    __host__ __device__ FastDiv() : magic(0), d(1) {}
+    __host__ explicit FastDiv(uint32_t dd) : magic(dd > 1 ? (uint32_t)((0x100000000ull + dd - 1) / dd) : 0u), d(dd) {}
+    __device__ __forceinline__ uint32_t div(uint32_t x) const { return d == 1 ? x : __umulhi(x, magic); }
+};
+
 struct RadixList {
     int n_pass;
     int radix[kMaxRadixPasses];
+    FastDiv div_m[kMaxRadixPasses];    // by n2 / radix[p]   (butterflies per frame)
+    FastDiv div_ns[kMaxRadixPasses];   // by the product of the radices before pass p
+    FastDiv div_nf;                    // by the number of frames in a full tile
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -76,7 +87,7 @@ __device__ __forceinline__ void butterfly<5>(float2 (&v)[5]) {
 // One Stockham pass of radix R over `nf` frames.  FIRST: inputs come from the windowed
 // sample segment (even samples -> real, odd -> imaginary part of the half-size sequence).
 template <int R, bool FIRST>
-__device__ __forceinline__ void stockham_pass(int nf, int n2, int Ns, int hop, int zs,
+__device__ __forceinline__ void stockham_pass(int nf, int n2, int Ns, FastDiv dm, FastDiv dns, int hop, int zs,
                                               const float* __restrict__ s_samp,
                                               const float* __restrict__ s_win,
                                               const float2* __restrict__ s_tw,
@@ -85,16 +96,18 @@ __device__ __forceinline__ void stockham_pass(int nf, int n2, int Ns, int hop, i
     const int total = nf * m;
     const int step = n2 / (Ns * R);
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int fr = idx / m;
+        const int fr = (int)dm.div((uint32_t)idx);
         const int j = idx - fr * m;
-        const int k = j % Ns;
+        const int k = j - (int)dns.div((uint32_t)j) * Ns;
         float2 v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const int n = j + q * m;
             if (FIRST) {
-                const float* x = s_samp + fr * hop + 2 * n;
-                v[q] = make_float2(x[0] * s_win[2 * n], x[1] * s_win[2 * n + 1]);
+                // hop is even on this path (odd hops use the scalar variant below): 8-byte loads
+                const float2 x = *reinterpret_cast<const float2*>(s_samp + fr * hop + 2 * n);
+                const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
+                v[q] = make_float2(x.x * w.x, x.y * w.y);
             } else {
                 v[q] = in[fr * zs + n];
                 if (q > 0) v[q] = cmul(v[q], s_tw[q * k * step]);
@@ -108,14 +121,14 @@ __device__ __forceinline__ void stockham_pass(int nf, int n2, int Ns, int hop, i
 }
 
 template <bool FIRST>
-__device__ __forceinline__ void run_pass(int R, int nf, int n2, int Ns, int hop, int zs,
+__device__ __forceinline__ void run_pass(int R, int nf, int n2, int Ns, FastDiv dm, FastDiv dns, int hop, int zs,
                                          const float* s_samp, const float* s_win, const float2* s_tw,
                                          const float2* in, float2* out) {
     switch (R) {
-        case 2: stockham_pass<2, FIRST>(nf, n2, Ns, hop, zs, s_samp, s_win, s_tw, in, out); break;
-        case 3: stockham_pass<3, FIRST>(nf, n2, Ns, hop, zs, s_samp, s_win, s_tw, in, out); break;
-        case 4: stockham_pass<4, FIRST>(nf, n2, Ns, hop, zs, s_samp, s_win, s_tw, in, out); break;
-        default: stockham_pass<5, FIRST>(nf, n2, Ns, hop, zs, s_samp, s_win, s_tw, in, out); break;
+        case 2: stockham_pass<2, FIRST>(nf, n2, Ns, dm, dns, hop, zs, s_samp, s_win, s_tw, in, out); break;
+        case 3: stockham_pass<3, FIRST>(nf, n2, Ns, dm, dns, hop, zs, s_samp, s_win, s_tw, in, out); break;
+        case 4: stockham_pass<4, FIRST>(nf, n2, Ns, dm, dns, hop, zs, s_samp, s_win, s_tw, in, out); break;
+        default: stockham_pass<5, FIRST>(nf, n2, Ns, dm, dns, hop, zs, s_samp, s_win, s_tw, in, out); break;
     }
 }
 
@@ -169,12 +182,12 @@ stft_mag_kernel(const float* __restrict__ wave, const int64_t* __restrict__ samp
     float2* in = bufB;
     float2* out = bufA;
     int Ns = 1;
-    run_pass<true>(rl.radix[0], nf, n2, Ns, hop, zs, s_samp, s_win, s_twh, in, out);
+    run_pass<true>(rl.radix[0], nf, n2, Ns, rl.div_m[0], rl.div_ns[0], hop, zs, s_samp, s_win, s_twh, in, out);
     Ns *= rl.radix[0];
     __syncthreads();
     for (int p = 1; p < rl.n_pass; ++p) {
         float2* t = in; in = out; out = t;
-        run_pass<false>(rl.radix[p], nf, n2, Ns, hop, zs, s_samp, s_win, s_twh, in, out);
+        run_pass<false>(rl.radix[p], nf, n2, Ns, rl.div_m[p], rl.div_ns[p], hop, zs, s_samp, s_win, s_twh, in, out);
         Ns *= rl.radix[p];
         __syncthreads();
     }
@@ -184,7 +197,7 @@ stft_mag_kernel(const float* __restrict__ wave, const int64_t* __restrict__ samp
     const int64_t base = (int64_t)F * fo + t0;
     const int total = F * nf;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int k = idx / nf;
+        const int k = (nf == TT) ? (int)rl.div_nf.div((uint32_t)idx) : idx / nf;   // partial last tile: plain division
         const int fr = idx - k * nf;
         const float2 zk = Z[fr * zs + (k == n2 ? 0 : k)];
         float2 zc = Z[fr * zs + (k == 0 ? 0 : n2 - k)];
@@ -239,9 +252,24 @@ int launch_stft(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* 
     int rc = ensure_stft_tiles(b, tt);
     if (rc) return rc;
     if (b->n_stft_tiles == 0) return HPSS_OK;
+    if (hop & 1) {
+        set_error("hop_length=%d must be even (8-byte sample loads in the FFT's first pass)", hop);
+        return HPSS_ERR_UNSUPPORTED;
+    }
     RadixList rl;
     rl.n_pass = plan->n_pass;
-    for (int i = 0; i < kMaxRadixPasses; ++i) rl.radix[i] = plan->radix[i];
+    {
+        int ns = 1;
+        for (int i = 0; i < kMaxRadixPasses; ++i) {
+            rl.radix[i] = plan->radix[i];
+            if (i < plan->n_pass) {
+                rl.div_m[i] = FastDiv((uint32_t)(plan->n2 / plan->radix[i]));
+                rl.div_ns[i] = FastDiv((uint32_t)ns);
+                ns *= plan->radix[i];
+            }
+        }
+        rl.div_nf = FastDiv((uint32_t)tt);
+    }
     const size_t smem = stft_smem_bytes(plan->n_fft, hop, tt);
     HPSS_CUDA(cudaFuncSetAttribute(stft_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     stft_mag_kernel<<<b->n_stft_tiles, 256, smem, st>>>(
