@@ -144,7 +144,8 @@ HPSS_API int hpss_median_freq(hpss_ctx* ctx, const hpss_batch* batch, const floa
  * 408-412, 418-424, 430-434, 440-444).
  *   mel_dev == NULL  -> identity projection, out rows = 2*rows  (HARMPERC / LOG_HARMPERC)
  *   mel_dev != NULL  -> dense float32 (n_mels, rows) basis,  out rows = 2*n_mels
- *   log_power != 0   -> 10*log10(max(amin, x*x)); clip_max_dev[2*c+s] (ordered-uint
+ *   log_power == 1   -> 10*log10(max(amin, x*x))  (the reference always calls power_to_db(x**2));
+ *   log_power == 2   -> 10*log10(max(amin, x));    either way clip_max_dev[2*c+s] (ordered-uint
  *                       encoding, zero-initialised by this call) receives the per-clip,
  *                       per-stream maximum needed by top_db.
  * harm_dev/perc_dev may be NULL together: plain single-stream mode on S (SPEC family),
@@ -200,7 +201,7 @@ HPSS_API int hpss_scale_data(hpss_ctx* ctx, const hpss_batch* batch, const float
 
 /* ---- N1: get_feature_patches (lib/preprocessing.py:137-292 + tools.pyx:21-38) for one
  * clip-batch: optional per-clip per-row standardisation (sklearn StandardScaler: mean,
- * std ddof=0 in float64, zero std -> 1, float32 result) followed by the patch gather.
+ * std ddof=0 in float64, constant rows -> scale 1, float32 update) followed by the patch gather.
  *   hpss_row_standardize: in place on feat_dev (D, T_c) per clip.
  *   hpss_extract_patches: clip `clip` only; patch p covers frames
  *       [p*shift, p*shift + patch_size), p < n_patches = len(range(W/2, T - W/2, shift));

@@ -96,16 +96,21 @@ def extract_patches(FV, patch_size, patch_shift):
 
 
 def _standard_scale_rows(FV):
-    """StandardScaler(copy=False).fit_transform(FV.T).T on float32 rows:
-    per-row mean / std (ddof=0) in float64, zero std -> 1, then the in-place
-    float32 updates ``X -= mean; X /= scale`` (each computed in f64, rounded to f32)."""
+    """StandardScaler(copy=False).fit_transform(FV.T).T on float32 rows, as the sklearn installed
+    here (1.9, the only pin available) does it: per-row mean / variance (ddof=0) in float64, constant
+    rows keep scale 1, then ``X -= mean.astype(X.dtype); X /= scale.astype(X.dtype)`` in float32.
+    (sklearn of the reference's era applied the float64 mean/scale directly; the two differ by at
+    most ~2 float32 ulp.)"""
     FV = np.array(FV, dtype=np.float32, copy=True)
+    n = FV.shape[1]
     mean = FV.astype(np.float64).mean(axis=1)
     var = FV.astype(np.float64).var(axis=1)
+    eps = np.finfo(np.float64).eps
+    constant = var <= n * eps * var + (n * mean * eps) ** 2          # sklearn _is_constant_feature
     scale = np.sqrt(var)
-    scale[scale == 0.0] = 1.0
-    FV -= mean[:, None]
-    FV /= scale[:, None]
+    scale[constant] = 1.0
+    FV -= mean.astype(np.float32)[:, None]
+    FV /= scale.astype(np.float32)[:, None]
     return FV
 
 

@@ -69,7 +69,7 @@ __device__ __forceinline__ void softmask_apply(float s, float h, float p, float&
 
 __device__ __forceinline__ float post_value(float x, int log_power, float amin) {
     if (!log_power) return x;
-    const float x2 = __fmul_rn(x, x);
+    const float x2 = (log_power == 2) ? x : __fmul_rn(x, x);   // 2: x already is a power
     return 3.0102999566398120f * __log2f(fmaxf(amin, x2));   // 10*log10(x), MUFU.LG2: |err| ~ 1e-6 dB
 }
 

@@ -103,8 +103,8 @@ scale_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_o
 }
 
 // sklearn.preprocessing.StandardScaler(copy=False).fit_transform on one clip's rows:
-// float64 two-pass mean / variance (ddof=0), constant rows keep scale 1, then the in-place
-// float32 updates X -= mean; X /= scale (each evaluated in float64 and rounded to float32).
+// float64 two-pass mean / variance (ddof=0), constant rows keep scale 1, then the in-place float32
+// updates X -= float32(mean); X /= float32(scale) (what sklearn 1.9 does for float32 input).
 // One warp per (clip, row) line.
 __global__ void __launch_bounds__(kThreads)
 row_standardize_kernel(float* __restrict__ feat, const int64_t* __restrict__ frame_off, int n_clips, int D) {
@@ -129,10 +129,8 @@ row_standardize_kernel(float* __restrict__ feat, const int64_t* __restrict__ fra
         const double eps = 2.220446049250313e-16;
         const double ub = (double)T * eps * var + ((double)T * mean * eps) * ((double)T * mean * eps);
         const double scale = (var <= ub) ? 1.0 : sqrt(var);
-        for (int t = lane; t < T; t += 32) {
-            const float x1 = (float)((double)x[t] - mean);
-            x[t] = (float)((double)x1 / scale);
-        }
+        const float mean32 = (float)mean, scale32 = (float)scale;   // X -= mean.astype(f32); X /= scale.astype(f32)
+        for (int t = lane; t < T; t += 32) x[t] = __fdiv_rn(__fsub_rn(x[t], mean32), scale32);
     }
 }
 

@@ -195,7 +195,7 @@ def mask_mel_log(batch: Batch, S: torch.Tensor, harm: Optional[torch.Tensor], pe
     check(batch.lib.hpss_mask_mel_log(batch.ctx.handle, batch.handle, _dev_ptr(S, torch.float32, "S"),
                                       _dev_ptr(harm, torch.float32, "harm"), _dev_ptr(perc, torch.float32, "perc"),
                                       int(rows), _dev_ptr(mel, torch.float32, "mel"), n_mels, int(bool(pre_square)),
-                                      int(bool(log_power)), float(amin), _dev_ptr(out), _dev_ptr(clip_max),
+                                      int(log_power), float(amin), _dev_ptr(out), _dev_ptr(clip_max),
                                       _stream_ptr()))
     return out, clip_max
 

@@ -118,17 +118,19 @@ def main():
                                   "LogMelHarmPercSpec", save_feat=False)
     out["fv:music:LogMelHarmPercSpec"] = fvm
 
+    # NOTE: the reference standardises IN PLACE (StandardScaler(copy=False) on views of FV), i.e.
+    # get_feature_patches mutates its argument; copies keep the golden featuregrams pristine.
     # patches: Lemaire (no trailing axis) and a CNN model (expand_dims), incl. the T < patch_size tiling
     FV = out["fv:speech:LogMelHarmPercSpec"]
     for mdl in ("Lemaire_et_al_MTL", "Doukhan_et_al_MTL"):
         P = dict(PARAMS, Model=mdl)
         for fn in ("LogMelHarmPercSpec", "LogMelHarmSpec", "LogMelPercSpec"):
             for (W, sh) in [(68, 68), (49, 24), (249, 24)]:
-                out[f"patch:{mdl}:{fn}:{W}:{sh}"] = preproc.get_feature_patches(P, FV, W, sh, fn)
+                out[f"patch:{mdl}:{fn}:{W}:{sh}"] = preproc.get_feature_patches(P, FV.copy(), W, sh, fn)
     out["patch:Doukhan_et_al_MTL:Spec:21:21"] = preproc.get_feature_patches(
-        dict(PARAMS, Model="Doukhan_et_al_MTL"), out["fv:speech:Spec"], 21, 21, "Spec")
+        dict(PARAMS, Model="Doukhan_et_al_MTL"), out["fv:speech:Spec"].copy(), 21, 21, "Spec")
     P = dict(PARAMS, Model="Lemaire_et_al_MTL", frame_level_scaling=True)
-    out["patch:fls:LogMelHarmPercSpec:49:24"] = preproc.get_feature_patches(P, FV, 49, 24, "LogMelHarmPercSpec")
+    out["patch:fls:LogMelHarmPercSpec:49:24"] = preproc.get_feature_patches(P, FV.copy(), 49, 24, "LogMelHarmPercSpec")
 
     # global statistics over cached featuregrams (the reference np.load()s them from feature_opDir)
     import tempfile

@@ -1,0 +1,218 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what the header declares, the
+host-only entry points agree with the oracle, compute calls fail loudly without a GPU, the
+reference-signature mirror's host logic (name dispatch, signal preparation) matches the golden
+vectors made by the reference's own code, clip sharding and the moments all-reduce (gloo, world 2)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import librosa_restated as lr
+from oracle import preprocessing_oracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "reference_glue.npz")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from sm_hpss_mtl_b200 import _lib
+    return _lib.load()
+
+
+# ------------------------------------------------------------------ C ABI surface
+def test_library_exports_every_header_symbol(lib):
+    from sm_hpss_mtl_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "hpss_b200.h")).read()
+    declared = set(re.findall(r"HPSS_API\s+[\w\s\*]+?\b(hpss_\w+)\s*\(", header))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/hpss_b200.h but not exported"
+    assert declared == set(_lib.PROTOTYPES), "ctypes prototypes and header are out of sync"
+    assert b"sm_100a" in lib.hpss_version()
+
+
+def test_params_struct_layout():
+    from sm_hpss_mtl_b200._lib import Params
+    assert C.sizeof(Params) == 8 * 4 + 2 * 4
+    assert [f[0] for f in Params._fields_] == ["n_fft", "win_length", "hop_length", "l_harm", "l_perc", "n_mels",
+                                               "mel_sr", "feature", "amin", "top_db"]
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the context cannot be created and the Python API refuses to run."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from sm_hpss_mtl_b200 import _lib, engine
+    h = C.c_void_p()
+    rc = lib.hpss_ctx_create(0, C.byref(h))
+    assert rc == _lib.ERR_CUDA and not h.value
+    assert b"no CPU fallback" in lib.hpss_last_error()
+    with pytest.raises(RuntimeError):
+        engine.get_context()
+    from sm_hpss_mtl_b200 import preprocessing as pp
+    with pytest.raises(RuntimeError):
+        pp.featuregram_from_signal(np.zeros(16000, np.float32), 16000, {"Tw": 25, "Ts": 10, "Model": "m",
+                                   "l_harm": {"m": 21}, "l_perc": {"m": 11}}, 400, 120, "LogMelHarmPercSpec")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "sm_hpss_mtl_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+# ------------------------------------------------------------------ host-only entry points
+@pytest.mark.parametrize("sr,n_fft,n_mels", [(22050, 400, 120), (16000, 400, 120), (22050, 512, 21), (22050, 2048, 128),
+                                             (22050, 400, 40)])
+def test_mel_filterbank_matches_oracle(sr, n_fft, n_mels):
+    from sm_hpss_mtl_b200 import engine
+    got, want = engine.mel_filterbank(sr, n_fft, n_mels), lr.mel(sr, n_fft, n_mels)
+    assert got.shape == want.shape and float(np.abs(got - want).max()) <= 1e-7
+    assert np.array_equal(got > 0, want > 0)
+
+
+@pytest.mark.parametrize("n_fft,win", [(400, 400), (512, 400), (2048, 2048), (512, 401)])
+def test_stft_window_matches_oracle(n_fft, win):
+    from sm_hpss_mtl_b200 import engine
+    want = lr.pad_center(lr.hann_periodic(win), n_fft).astype(np.float32)
+    assert float(np.abs(engine.stft_window(n_fft, win) - want).max()) <= 6e-8
+
+
+def test_num_patches_and_feature_rows(lib):
+    from sm_hpss_mtl_b200 import engine
+    for T in (68, 69, 98, 249, 250, 998, 5000):
+        for (W, sh) in [(249, 24), (68, 68), (99, 34), (99, 1), (21, 5)]:
+            assert engine.num_patches(T, W, sh) == len(range(W // 2, T - W // 2, sh))
+    rows = {"SPEC": 201, "LOGSPEC": 201, "MELSPEC": 120, "LOGMELSPEC": 120, "HARMPERC": 402, "LOG_HARMPERC": 402,
+            "MEL_HARMPERC": 240, "LOGMEL_HARMPERC": 240}
+    for f, r in rows.items():
+        assert engine.feature_rows(engine.make_params(feature=f)) == r
+
+
+def test_stats_finalize_closed_form_matches_two_pass():
+    from sm_hpss_mtl_b200 import engine
+    rng = np.random.default_rng(0)
+    D, names = 17, ["music", "speech", "speech_music"]
+    groups = {n: [(rng.standard_normal((D, int(rng.integers(20, 90)))) * 6 - 35).astype(np.float32) for _ in range(3)]
+              for n in names}
+    acc = np.zeros(3 * D + D + 3 + 1)
+    for k, n in enumerate(names):
+        for fv in groups[n]:
+            acc[k * D:(k + 1) * D] += fv.astype(np.float64).sum(axis=1)
+            acc[3 * D:4 * D] += (fv.astype(np.float64) ** 2).sum(axis=1)
+            acc[4 * D + k] += fv.shape[1]
+    mean, std, counts, bad = engine.stats_finalize(acc, D, 3)
+    want_mean, want_std, n0, n1, n2 = po.get_data_stats(groups, names)
+    assert list(counts) == [n0, n1, n2] and bad == 0
+    assert np.allclose(mean, want_mean, rtol=1e-6, atol=1e-6) and np.allclose(std, want_std, rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------ reference-signature mirror (host logic)
+def test_feature_name_dispatch():
+    from sm_hpss_mtl_b200.preprocessing import feature_family
+    table = {"Spec": "SPEC", "LogSpec": "LOGSPEC", "MelSpec": "MELSPEC", "LogMelSpec": "LOGMELSPEC",
+             "HarmSpec": "HARMPERC", "PercSpec": "HARMPERC", "HarmPercSpec": "HARMPERC",
+             "LogHarmSpec": "LOG_HARMPERC", "LogPercSpec": "LOG_HARMPERC", "LogHarmPercSpec": "LOG_HARMPERC",
+             "MelHarmSpec": "MEL_HARMPERC", "MelPercSpec": "MEL_HARMPERC", "MelHarmPercSpec": "MEL_HARMPERC",
+             "LogMelHarmSpec": "LOGMEL_HARMPERC", "LogMelPercSpec": "LOGMEL_HARMPERC",
+             "LogMelHarmPercSpec": "LOGMEL_HARMPERC"}
+    for name, fam in table.items():
+        assert feature_family(name)[0] == fam
+        assert feature_family(name)[1] == (name in ("MelSpec", "LogMelSpec"))      # only these pass sr=fs
+    with pytest.raises(ValueError):
+        feature_family("MFCC")                                                     # not in the reference
+
+
+def test_signal_preparation_matches_reference(tmp_path):
+    """normalise -> RMS -> silence removal (Cython semantics, incl. the tail of ones) -> normalise, and
+    SMR mixing, against the signals the reference's own functions produced."""
+    from sm_hpss_mtl_b200 import preprocessing as pp
+    g = np.load(GOLDEN)
+    audio = {k[len("audio:"):]: g[k] for k in g.files if k.startswith("audio:")}
+    for path, x in audio.items():
+        got, fs = pp.load_and_preprocess_signal(path, 25, 10, loader=lambda p: audio[p].copy())
+        want = g["prep:" + path]
+        assert fs == 16000 and got.shape == want.shape
+        assert np.allclose(got, want, rtol=0, atol=1e-7), path
+    sp0 = g["prep:/d/speech/sp0.wav"]
+    assert not np.array_equal(sp0, pp.normalize_signal(audio["/d/speech/sp0.wav"]))   # silence really was removed
+    mix = pp.mix_signals(sp0, g["prep:/d/music/mu0.wav"], 5)
+    assert np.allclose(mix, g["mix:sp0+mu0@5"], rtol=0, atol=1e-6)
+
+
+def test_load_audio_wav_roundtrip(tmp_path):
+    from scipy.io import wavfile
+    from sm_hpss_mtl_b200 import preprocessing as pp
+    x = (np.random.default_rng(0).standard_normal(4000) * 3000).astype(np.int16)
+    p = str(tmp_path / "a.wav")
+    wavfile.write(p, 16000, x)
+    y = pp.load_audio(p)
+    assert y.dtype == np.float32 and np.array_equal(y, x.astype(np.float32) / 32768.0)
+
+
+# ------------------------------------------------------------------ sharding + the one collective
+def test_shard_clips_properties():
+    from sm_hpss_mtl_b200.dist import shard_clips
+    rng = np.random.default_rng(1)
+    for n, w in [(1086, 8), (4096, 8), (5, 8), (1, 1), (100, 3), (0, 4)]:
+        lens = rng.integers(1600, 5_000_000, size=n)
+        sh = shard_clips(lens, w)
+        assert len(sh) == w and sh[0][0] == 0 and sh[-1][1] == n
+        assert all(a <= b for a, b in sh) and all(sh[i][1] == sh[i + 1][0] for i in range(w - 1))
+        if n >= 50 * w:
+            tot = [int(lens[a:b].sum()) for a, b in sh]
+            assert max(tot) - min(tot) <= 2 * int(lens.max())
+    assert shard_clips([16000] * 4096, 8) == [(i * 512, (i + 1) * 512) for i in range(8)]
+
+
+def _gloo_worker(rank, world, port, D, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sm_hpss_mtl_b200 import dist as hd
+    from sm_hpss_mtl_b200.dist import shard_clips
+    rng = np.random.default_rng(7)
+    fvs = [(rng.standard_normal((D, int(rng.integers(10, 60)))) * 5 - 30).astype(np.float32) for _ in range(12)]
+    cls = [i % 3 for i in range(12)]
+    a, b = shard_clips([fv.shape[1] for fv in fvs], world)[rank]
+    acc = np.zeros(hd.moments_size(D, 3))
+    for fv, k in zip(fvs[a:b], cls[a:b]):                      # what hpss_moments accumulates on a GPU
+        acc[k * D:(k + 1) * D] += fv.astype(np.float64).sum(axis=1)
+        acc[3 * D:4 * D] += (fv.astype(np.float64) ** 2).sum(axis=1)
+        acc[4 * D + k] += fv.shape[1]
+    t = torch.from_numpy(acc)
+    hd.allreduce_moments(t)
+    mean, std, counts = hd.finalize_stats(t.numpy(), D, 3)
+    if rank == 0:
+        q.put((mean, std, counts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_moments_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    D, world = 11, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, D, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    mean, std, counts = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(7)
+    fvs = [(rng.standard_normal((D, int(rng.integers(10, 60)))) * 5 - 30).astype(np.float32) for _ in range(12)]
+    names = ["music", "speech", "speech_music"]
+    groups = {n: [fvs[i] for i in range(12) if i % 3 == k] for k, n in enumerate(names)}
+    want_mean, want_std, n0, n1, n2 = po.get_data_stats(groups, names)
+    assert [int(c) for c in counts] == [n0, n1, n2]
+    assert np.allclose(mean, want_mean, rtol=1e-6, atol=1e-6) and np.allclose(std, want_std, rtol=1e-6, atol=1e-6)
