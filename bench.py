@@ -7,7 +7,7 @@
 Workload (BASELINE.json configs[1]): a batch of 4096 synthetic 1 s 16 kHz segments per GPU,
 n_fft = 400, hop = 160, median kernels 31/31, 120 mel bands, feature LogMelHarmPercSpec.
 One step = waveform -> (240, 98) float32 featuregram for every clip of the batch + the raw
-feature moments of get_data_stats (all-reduced over ranks when N > 1: the only collective).
+feature moments of get_data_stats (hpss_featuregram_moments) (all-reduced over ranks when N > 1: the only collective).
 
   value  device-resident waveform -> device-resident features, CUDA events on the launching
          stream, max over ranks; inputs (262 MB) + intermediates (1.3 GB/step) exceed the
@@ -185,9 +185,8 @@ def run_gpu(args):
     acc = torch.zeros(3 * D + D + 3 + 1, dtype=torch.float64, device="cuda")
 
     def step():
-        engine.featuregram(batch, wave, prm, out=out)
         acc.zero_()
-        engine.moments(batch, out, D, classes, 3, acc=acc)
+        engine.featuregram_moments(batch, wave, prm, classes, 3, out=out, acc=acc)
         if world > 1:
             allreduce_moments(acc)
 
@@ -238,8 +237,8 @@ def run_gpu(args):
     stages = None
     if rank == 0:
         mel = torch.from_numpy(engine.mel_filterbank(22050, CFG["n_fft"], M)).cuda()
-        names = ["K1 stft_mag", "K2h median_time", "K2p median_freq", "K3 mask_mel_log", "K3b topdb_clip", "K5 moments"]
-        bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F, 12 * F + 8 * M, 16 * M, 8 * M]
+        names = ["K1 stft_mag", "K2h median_time", "K2p median_freq", "K3 mask_mel_log", "K3b+K5 topdb_moments"]
+        bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F, 12 * F + 8 * M, 16 * M]
         tot = [0.0] * len(names)
         reps = max(args.steps, 5)
         for it in range(reps + 2):
@@ -249,9 +248,8 @@ def run_gpu(args):
             harm = engine.median_time(batch, S, F, CFG["l_harm"]); evs[2].record()
             perc = engine.median_freq(batch, S, F, CFG["l_perc"]); evs[3].record()
             o, cmax = engine.mask_mel_log(batch, S, harm, perc, F, mel=mel, log_power=True); evs[4].record()
-            engine.topdb_clip(batch, o, M, 2, cmax, 80.0); evs[5].record()
             acc.zero_()
-            engine.moments(batch, o, D, classes, 3, acc=acc); evs[6].record()
+            engine.topdb_moments(batch, o, M, 2, cmax, 80.0, classes, 3, acc=acc); evs[5].record()
             torch.cuda.synchronize()
             if it >= 2:
                 for i in range(len(names)):
@@ -281,7 +279,7 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_gpu": n_clips, "frames_per_gpu": frames,
                        "l2": "inputs+intermediates per step (1.6 GB) exceed the 126 MB L2; no explicit flush",
-                       "step": "hpss_featuregram (K1,K2h,K2p,K3,K3b) + hpss_moments (K5)"
+                       "step": "hpss_featuregram_moments = K1, K2h, K2p, K3, K3b+K5 (top_db clip and moments share one pass)"
                                + (" + NCCL all-reduce of the 968-double moment vector" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(wave_host.nbytes),
                     "d2h_bytes_per_step": int(out_host.nbytes), "steps": e2e_steps,

@@ -187,6 +187,17 @@ HPSS_API int hpss_featuregram_host(hpss_ctx* ctx, const hpss_batch* batch, const
 HPSS_API int hpss_moments(hpss_ctx* ctx, const hpss_batch* batch, const float* feat_dev, int32_t D,
                           const int32_t* clip_class_host, int32_t n_classes, double* sum_dev,
                           double* sumsq_dev, double* count_dev, double* nonfinite_dev, void* stream);
+/* K3b + K5 in one pass over the features: hpss_topdb_clip followed by hpss_moments of the clipped values. */
+HPSS_API int hpss_topdb_moments(hpss_ctx* ctx, const hpss_batch* batch, float* out_dev, int32_t rows_per_stream,
+                                int32_t n_streams, const uint32_t* clip_max_dev, float top_db,
+                                const int32_t* clip_class_host, int32_t n_classes, double* sum_dev,
+                                double* sumsq_dev, double* count_dev, double* nonfinite_dev, void* stream);
+/* hpss_featuregram followed by hpss_moments in one call; when the feature has a top_db clip the
+ * clip and the moment accumulation share a single pass over the features (K3b + K5 fused). */
+HPSS_API int hpss_featuregram_moments(hpss_ctx* ctx, const hpss_batch* batch, const float* wave_dev,
+                                      const hpss_params* params, float* out_dev, const int32_t* clip_class_host,
+                                      int32_t n_classes, double* sum_dev, double* sumsq_dev, double* count_dev,
+                                      double* nonfinite_dev, void* stream);
 /* class means -> unweighted mean of class means (:530-536); stdev = sqrt(sum (x-mean)^2 /
  * (N-1)) (:575-583) from the raw moments, float64 -> float32 (:586). Host arrays. */
 HPSS_API int hpss_stats_finalize(const double* sum_host, const double* sumsq_host,

@@ -78,6 +78,8 @@ PROTOTYPES = {
     "hpss_featuregram_from_spec": (C.c_int, [_vp, _vp, _vp, _i32, C.POINTER(Params), _vp, _vp]),
     "hpss_featuregram_host": (C.c_int, [_vp, _vp, _vp, C.POINTER(Params), _vp]),
     "hpss_moments": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "hpss_topdb_moments": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "hpss_featuregram_moments": (C.c_int, [_vp, _vp, _vp, C.POINTER(Params), _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "hpss_stats_finalize": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "hpss_scale_data": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _f64, _vp, _vp]),
     "hpss_row_standardize": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),

@@ -278,9 +278,17 @@ static int check_params(const hpss_params* p) {
     return HPSS_OK;
 }
 
+// optional sink of the fused "top_db clip + feature moments" tail
+struct MomentSink {
+    const int32_t* d_class = nullptr;
+    int n_classes = 0;
+    double *sum = nullptr, *sumsq = nullptr, *count = nullptr, *nonfinite = nullptr;
+};
+
 // spectrogram -> features (everything after the STFT); S may alias nothing in the workspace
 static int features_from_spec(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, const hpss_params* p,
-                              float* harm, float* perc, uint32_t* clip_max, float* out, cudaStream_t st) {
+                              float* harm, float* perc, uint32_t* clip_max, float* out, cudaStream_t st,
+                              const MomentSink* ms = nullptr) {
     const int ns = feature_streams(p->feature);
     const bool is_mel = feature_is_mel(p->feature), is_log = feature_is_log(p->feature);
     MelPlan* mp = nullptr;
@@ -301,8 +309,16 @@ static int features_from_spec(hpss_ctx* ctx, const hpss_batch* b, const float* S
                          mp ? mp->d_w : nullptr, mp ? mp->d_band : nullptr, mp ? mp->n_mels : 0, pre_square,
                          is_log ? 1 : 0, p->amin, out, clip ? clip_max : nullptr, st);
     if (rc) return rc;
+    const int rps = is_mel ? p->n_mels : rows;
+    if (ms) {   // one pass: clip (if any) + moments
+        if (clip)
+            return launch_topdb_moments(ctx, b, out, rps, ns, clip_max, p->top_db, ms->d_class, ms->n_classes, ms->sum,
+                                        ms->sumsq, ms->count, ms->nonfinite, st);
+        return launch_moments(ctx, b, out, rps * ns, ms->d_class, ms->n_classes, ms->sum, ms->sumsq, ms->count,
+                              ms->nonfinite, st);
+    }
     if (clip) {
-        rc = launch_topdb(ctx, b, out, is_mel ? p->n_mels : rows, ns, clip_max, p->top_db, st);
+        rc = launch_topdb(ctx, b, out, rps, ns, clip_max, p->top_db, st);
         if (rc) return rc;
     }
     return HPSS_OK;
@@ -330,7 +346,7 @@ static int carve_workspace(hpss_ctx* ctx, const hpss_batch* b, int rows, bool ne
 }
 
 static int featuregram_device(hpss_ctx* ctx, hpss_batch* b, const float* wave, const hpss_params* p, float* out,
-                              cudaStream_t st) {
+                              cudaStream_t st, const MomentSink* ms = nullptr) {
     int rc = check_params(p);
     if (rc) return rc;
     if (!b->has_samples) { set_error("batch was built from frame counts; waveform entry needs sample lengths"); return HPSS_ERR_INVALID; }
@@ -342,13 +358,18 @@ static int featuregram_device(hpss_ctx* ctx, hpss_batch* b, const float* wave, c
     rc = get_fft_plan(ctx, p->n_fft, p->win_length, &plan);
     if (rc) return rc;
     const int rows = p->n_fft / 2 + 1;
-    if (p->feature == HPSS_FEAT_SPEC) return launch_stft(ctx, b, wave, plan, p->hop_length, 0, out, nullptr, st);
+    if (p->feature == HPSS_FEAT_SPEC) {
+        rc = launch_stft(ctx, b, wave, plan, p->hop_length, 0, out, nullptr, st);
+        if (rc || !ms) return rc;
+        return launch_moments(ctx, b, out, rows, ms->d_class, ms->n_classes, ms->sum, ms->sumsq, ms->count,
+                              ms->nonfinite, st);
+    }
     Workspace w;
     rc = carve_workspace(ctx, b, rows, true, feature_streams(p->feature) == 2, 0, &w, nullptr);
     if (rc) return rc;
     rc = launch_stft(ctx, b, wave, plan, p->hop_length, 0, w.S, nullptr, st);
     if (rc) return rc;
-    return features_from_spec(ctx, b, w.S, rows, p, w.harm, w.perc, w.clip_max, out, st);
+    return features_from_spec(ctx, b, w.S, rows, p, w.harm, w.perc, w.clip_max, out, st, ms);
 }
 
 }  // namespace hpss
@@ -687,18 +708,54 @@ int hpss_featuregram_host(hpss_ctx* ctx, const hpss_batch* batch, const float* w
     return HPSS_OK;
 }
 
+static int upload_classes(hpss_batch* b, const int32_t* clip_class, int n_classes, cudaStream_t st) {
+    for (int c = 0; c < b->n_clips; ++c)
+        if (clip_class[c] < 0 || clip_class[c] >= n_classes) { set_error("clip %d has class %d outside [0,%d)", c, clip_class[c], n_classes); return HPSS_ERR_INVALID; }
+    if (!b->d_clip_class && b->n_clips > 0) HPSS_CUDA(cudaMalloc(&b->d_clip_class, sizeof(int32_t) * b->n_clips));
+    if (b->n_clips > 0)
+        HPSS_CUDA(cudaMemcpyAsync(b->d_clip_class, clip_class, sizeof(int32_t) * b->n_clips, cudaMemcpyHostToDevice, st));
+    return HPSS_OK;
+}
+
+int hpss_featuregram_moments(hpss_ctx* ctx, const hpss_batch* batch, const float* wave, const hpss_params* p,
+                             float* out, const int32_t* clip_class, int32_t n_classes, double* sum, double* sumsq,
+                             double* count, double* nonfinite, void* stream) {
+    if (!ctx || !batch || !wave || !out || !clip_class || !sum || !sumsq || !count || !nonfinite) { set_error("featuregram_moments: NULL argument"); return HPSS_ERR_INVALID; }
+    if (n_classes < 1) { set_error("featuregram_moments: n_classes=%d", n_classes); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    hpss_batch* b = const_cast<hpss_batch*>(batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_classes(b, clip_class, n_classes, st);
+    if (rc) return rc;
+    MomentSink ms;
+    ms.d_class = b->d_clip_class; ms.n_classes = n_classes;
+    ms.sum = sum; ms.sumsq = sumsq; ms.count = count; ms.nonfinite = nonfinite;
+    return featuregram_device(ctx, b, wave, p, out, st, &ms);
+}
+
+int hpss_topdb_moments(hpss_ctx* ctx, const hpss_batch* batch, float* out, int32_t rows_per_stream, int32_t n_streams,
+                       const uint32_t* clip_max, float top_db, const int32_t* clip_class, int32_t n_classes, double* sum,
+                       double* sumsq, double* count, double* nonfinite, void* stream) {
+    if (!ctx || !batch || !out || !clip_max || !clip_class || !sum || !sumsq || !count || !nonfinite) { set_error("topdb_moments: NULL argument"); return HPSS_ERR_INVALID; }
+    if (top_db < 0.f || rows_per_stream < 1 || n_streams < 1 || n_classes < 1) { set_error("topdb_moments: bad argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    hpss_batch* b = const_cast<hpss_batch*>(batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_classes(b, clip_class, n_classes, st);
+    if (rc) return rc;
+    return launch_topdb_moments(ctx, batch, out, rows_per_stream, n_streams, clip_max, top_db, b->d_clip_class, n_classes,
+                                sum, sumsq, count, nonfinite, st);
+}
+
 int hpss_moments(hpss_ctx* ctx, const hpss_batch* batch, const float* feat, int32_t D, const int32_t* clip_class,
                  int32_t n_classes, double* sum, double* sumsq, double* count, double* nonfinite, void* stream) {
     if (!ctx || !batch || !feat || !clip_class || !sum || !sumsq || !count || !nonfinite) { set_error("moments: NULL argument"); return HPSS_ERR_INVALID; }
     if (D < 1 || n_classes < 1) { set_error("moments: D=%d n_classes=%d", D, n_classes); return HPSS_ERR_INVALID; }
-    for (int c = 0; c < batch->n_clips; ++c)
-        if (clip_class[c] < 0 || clip_class[c] >= n_classes) { set_error("moments: clip %d has class %d outside [0,%d)", c, clip_class[c], n_classes); return HPSS_ERR_INVALID; }
     HPSS_CUDA(cudaSetDevice(ctx->device));
     hpss_batch* b = const_cast<hpss_batch*>(batch);
     cudaStream_t st = (cudaStream_t)stream;
-    if (!b->d_clip_class && b->n_clips > 0) HPSS_CUDA(cudaMalloc(&b->d_clip_class, sizeof(int32_t) * b->n_clips));
-    if (b->n_clips > 0)
-        HPSS_CUDA(cudaMemcpyAsync(b->d_clip_class, clip_class, sizeof(int32_t) * b->n_clips, cudaMemcpyHostToDevice, st));
+    int rc = upload_classes(b, clip_class, n_classes, st);
+    if (rc) return rc;
     return launch_moments(ctx, batch, feat, D, b->d_clip_class, n_classes, sum, sumsq, count, nonfinite, st);
 }
 

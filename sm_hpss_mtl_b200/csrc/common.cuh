@@ -118,6 +118,9 @@ int launch_topdb(hpss_ctx* ctx, const hpss_batch* b, float* out, int rows_per_st
 int launch_moments(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, const int32_t* d_class,
                    int n_classes, double* sum, double* sumsq, double* count, double* nonfinite,
                    cudaStream_t st);
+int launch_topdb_moments(hpss_ctx* ctx, const hpss_batch* b, float* feat, int rows_per_stream, int n_streams,
+                         const uint32_t* clip_max, float top_db, const int32_t* d_class, int n_classes, double* sum,
+                         double* sumsq, double* count, double* nonfinite, cudaStream_t st);
 int launch_scale(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, const float* mean,
                  const float* stdev, double eps, double* out, cudaStream_t st);
 int launch_row_standardize(hpss_ctx* ctx, const hpss_batch* b, float* feat, int D, cudaStream_t st);

@@ -23,12 +23,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 // for its whole life and walks the clips of its frame chunk (lanes along time, coalesced 128-byte
 // reads); per-lane float64 accumulators (one sum per class + the sum of squares) stay in
 // registers and are reduced across the warp once, at the end: 1 + n_classes float64 atomics per warp.
-template <int MAXC>
+// CLIP: fused K3b -- x = max(x, max_clip_stream - top_db) is applied (and written back) on the way.
+template <int MAXC, bool CLIP>
 __global__ void __launch_bounds__(kThreads)
-moments_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_off,
+moments_kernel(float* __restrict__ feat, const int64_t* __restrict__ frame_off,
                const int32_t* __restrict__ block_clip, int n_clips, int64_t total_frames, int64_t chunk_frames,
                int D, const int32_t* __restrict__ clip_class, int n_classes, double* __restrict__ g_sum,
-               double* __restrict__ g_sumsq, double* __restrict__ g_count, double* __restrict__ g_nonfinite) {
+               double* __restrict__ g_sumsq, double* __restrict__ g_count, double* __restrict__ g_nonfinite,
+               const uint32_t* __restrict__ clip_max, int rows_per_stream, int n_streams, float top_db) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int d = blockIdx.y * kWarps + warp;
     if (d < D) {
@@ -45,10 +47,13 @@ moments_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame
             const int64_t seg_end = min(g1, fe);
             const int T = (int)(fe - fo), len = (int)(seg_end - g0);
             const int cls = __ldg(clip_class + c);
-            const float* row = feat + (int64_t)D * fo + (int64_t)d * T + (g0 - fo);
+            float* row = feat + (int64_t)D * fo + (int64_t)d * T + (g0 - fo);
+            float thr = -INFINITY;
+            if (CLIP) thr = ordered_to_float(__ldg(clip_max + (size_t)n_streams * c + d / rows_per_stream)) - top_db;
             double ps = 0.0;
             for (int t = lane; t < len; t += 32) {
-                float x = __ldg(row + t);
+                float x = CLIP ? row[t] : __ldg(row + t);
+                if (CLIP && x < thr) { x = thr; row[t] = x; }
                 if (!isfinite(x)) { x = 0.f; ++bad; }
                 const double xd = (double)x;
                 ps += xd;
@@ -154,8 +159,10 @@ patches_kernel(const float* __restrict__ feat, int D, int64_t T, int W, int shif
 
 }  // namespace
 
-int launch_moments(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, const int32_t* d_class,
-                   int n_classes, double* sum, double* sumsq, double* count, double* nonfinite, cudaStream_t st) {
+static int launch_moments_impl(hpss_ctx* ctx, const hpss_batch* b, float* feat, int D, const int32_t* d_class,
+                               int n_classes, double* sum, double* sumsq, double* count, double* nonfinite,
+                               const uint32_t* clip_max, int rows_per_stream, int n_streams, float top_db,
+                               cudaStream_t st) {
     const int64_t total = b->frame_off[b->n_clips];
     if (total == 0) return HPSS_OK;
     if (n_classes > 8) {
@@ -170,14 +177,31 @@ int launch_moments(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D,
     if (chunk < 1024) chunk = 1024;
     const int64_t n_chunks = (total + chunk - 1) / chunk;
     dim3 grid((unsigned)n_chunks, (unsigned)row_groups);
-    if (n_classes <= 4)
-        moments_kernel<4><<<grid, kThreads, 0, st>>>(feat, b->d_frame_off, b->d_block_clip, b->n_clips, total, chunk, D,
-                                                     d_class, n_classes, sum, sumsq, count, nonfinite);
-    else
-        moments_kernel<8><<<grid, kThreads, 0, st>>>(feat, b->d_frame_off, b->d_block_clip, b->n_clips, total, chunk, D,
-                                                     d_class, n_classes, sum, sumsq, count, nonfinite);
+#define HPSS_MOMENTS_LAUNCH(MAXC, CLIP)                                                                              \
+    moments_kernel<MAXC, CLIP><<<grid, kThreads, 0, st>>>(feat, b->d_frame_off, b->d_block_clip, b->n_clips, total,  \
+                                                          chunk, D, d_class, n_classes, sum, sumsq, count, nonfinite, \
+                                                          clip_max, rows_per_stream, n_streams, top_db)
+    if (clip_max) {
+        if (n_classes <= 4) HPSS_MOMENTS_LAUNCH(4, true); else HPSS_MOMENTS_LAUNCH(8, true);
+    } else {
+        if (n_classes <= 4) HPSS_MOMENTS_LAUNCH(4, false); else HPSS_MOMENTS_LAUNCH(8, false);
+    }
+#undef HPSS_MOMENTS_LAUNCH
     HPSS_LAUNCHED("moments_kernel");
     return HPSS_OK;
+}
+
+int launch_moments(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, const int32_t* d_class,
+                   int n_classes, double* sum, double* sumsq, double* count, double* nonfinite, cudaStream_t st) {
+    return launch_moments_impl(ctx, b, const_cast<float*>(feat), D, d_class, n_classes, sum, sumsq, count, nonfinite,
+                               nullptr, 1, 1, 0.f, st);
+}
+
+int launch_topdb_moments(hpss_ctx* ctx, const hpss_batch* b, float* feat, int rows_per_stream, int n_streams,
+                         const uint32_t* clip_max, float top_db, const int32_t* d_class, int n_classes, double* sum,
+                         double* sumsq, double* count, double* nonfinite, cudaStream_t st) {
+    return launch_moments_impl(ctx, b, feat, rows_per_stream * n_streams, d_class, n_classes, sum, sumsq, count,
+                               nonfinite, clip_max, rows_per_stream, n_streams, top_db, st);
 }
 
 int launch_scale(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, const float* mean,

@@ -274,6 +274,46 @@ def moments(batch: Batch, feat: torch.Tensor, D: int, clip_class: Sequence[int],
     return acc
 
 
+def topdb_moments(batch: Batch, out: torch.Tensor, rows_per_stream: int, n_streams: int, clip_max: torch.Tensor,
+                  top_db: float, clip_class: Sequence[int], n_classes: int, acc: Optional[torch.Tensor] = None):
+    """top_db clip (in place) + moments of the clipped features in one pass (K3b + K5 fused)."""
+    D = rows_per_stream * n_streams
+    if acc is None:
+        acc = torch.zeros(n_classes * D + D + n_classes + 1, dtype=torch.float64, device=out.device)
+    cls = np.ascontiguousarray(clip_class, dtype=np.int32)
+    base = acc.data_ptr()
+    check(batch.lib.hpss_topdb_moments(batch.ctx.handle, batch.handle, _dev_ptr(out, torch.float32, "out"),
+                                       int(rows_per_stream), int(n_streams), _dev_ptr(clip_max), float(top_db),
+                                       C.c_void_p(cls.ctypes.data), int(n_classes), C.c_void_p(base),
+                                       C.c_void_p(base + 8 * n_classes * D), C.c_void_p(base + 8 * (n_classes * D + D)),
+                                       C.c_void_p(base + 8 * (n_classes * D + D + n_classes)), _stream_ptr()))
+    return acc
+
+
+def featuregram_moments(batch: Batch, wave: torch.Tensor, params: Params, clip_class: Sequence[int], n_classes: int,
+                        out: Optional[torch.Tensor] = None, acc: Optional[torch.Tensor] = None):
+    """featuregram + moments in one library call (top_db clip and moments share one pass).
+    Returns (out, acc) with ``acc`` laid out as in :func:`moments` (accumulated into when given)."""
+    rows = feature_rows(params)
+    D = rows
+    if out is None:
+        out = torch.empty(rows * batch.total_frames, dtype=torch.float32, device=wave.device)
+    n = n_classes * D + D + n_classes + 1
+    if acc is None:
+        acc = torch.zeros(n, dtype=torch.float64, device=wave.device)
+    cls = np.ascontiguousarray(clip_class, dtype=np.int32)
+    if cls.size != batch.n_clips:
+        raise ValueError("clip_class must have one entry per clip")
+    base = acc.data_ptr()
+    check(batch.lib.hpss_featuregram_moments(batch.ctx.handle, batch.handle, _dev_ptr(wave, torch.float32, "wave"),
+                                             C.byref(params), _dev_ptr(out, torch.float32, "out"),
+                                             C.c_void_p(cls.ctypes.data), int(n_classes), C.c_void_p(base),
+                                             C.c_void_p(base + 8 * n_classes * D),
+                                             C.c_void_p(base + 8 * (n_classes * D + D)),
+                                             C.c_void_p(base + 8 * (n_classes * D + D + n_classes)), _stream_ptr()))
+    return out, acc
+
+
 def stats_finalize(acc_host: np.ndarray, D: int, n_classes: int):
     acc_host = np.ascontiguousarray(acc_host, dtype=np.float64)
     mean = np.empty(D, dtype=np.float32)

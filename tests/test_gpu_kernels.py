@@ -254,3 +254,19 @@ def test_row_standardize_and_patches(ctx):
             wantp = po.extract_patches(got.cpu().numpy(), W, shift)
             assert p.dtype == np.float64 and p.shape == wantp.shape
             assert np.array_equal(p, wantp)
+
+
+def test_featuregram_moments_fused_equals_separate(ctx):
+    Ls = [16000] * 9 + [4000, 30000]
+    cls = [i % 3 for i in range(len(Ls))]
+    wave = to_dev(np.concatenate([synth.synth_clip(50 + i, L) for i, L in enumerate(Ls)]))
+    for feat in ("LOGMEL_HARMPERC", "MEL_HARMPERC", "LOGSPEC", "SPEC"):
+        prm = engine.make_params(l_harm=31, l_perc=31, feature=feat)
+        batch = engine.Batch(ctx, clip_lengths=Ls, n_fft=400, hop_length=160)
+        D = engine.feature_rows(prm)
+        ref = engine.featuregram(batch, wave, prm)
+        acc_ref = engine.moments(batch, ref, D, cls, 3)
+        out, acc = engine.featuregram_moments(batch, wave, prm, cls, 3)
+        assert torch.equal(out, ref), feat
+        a, b = acc.cpu().numpy(), acc_ref.cpu().numpy()
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-9), feat
