@@ -236,9 +236,14 @@ def run_gpu(args):
     # ---- per-stage pass (rank 0 only reports it): same batch, one CUDA-event pair per kernel
     stages = None
     if rank == 0:
-        mel = torch.from_numpy(engine.mel_filterbank(22050, CFG["n_fft"], M)).cuda()
-        names = ["K1 stft_mag", "K2h median_time", "K2p median_freq", "K3 mask_mel_log", "K3b+K5 topdb_moments"]
-        bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F, 12 * F + 8 * M, 16 * M]
+        fused = os.environ.get("HPSS_USE_FUSED", "0") not in ("", "0")     # the path hpss_featuregram takes
+        if fused:
+            names = ["K1 stft_mag", "K2h median_time", "K2p+K3 perc_mask_mel_log", "K3b+K5 topdb_moments"]
+            bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F + 8 * M, 16 * M]
+        else:
+            names = ["K1 stft_mag", "K2h median_time", "K2p median_freq", "K3 mask_mel_log", "K3b+K5 topdb_moments"]
+            bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F, 12 * F + 8 * M, 16 * M]
+            mel = torch.from_numpy(engine.mel_filterbank(22050, CFG["n_fft"], M)).cuda()
         tot = [0.0] * len(names)
         reps = max(args.steps, 5)
         for it in range(reps + 2):
@@ -246,15 +251,21 @@ def run_gpu(args):
             evs[0].record()
             S = engine.stft_mag(batch, wave, CFG["n_fft"], CFG["win"], CFG["hop"]); evs[1].record()
             harm = engine.median_time(batch, S, F, CFG["l_harm"]); evs[2].record()
-            perc = engine.median_freq(batch, S, F, CFG["l_perc"]); evs[3].record()
-            o, cmax = engine.mask_mel_log(batch, S, harm, perc, F, mel=mel, log_power=True); evs[4].record()
+            if fused:
+                o, cmax = engine.perc_mask_mel_log(batch, S, harm, F, CFG["l_perc"], 22050, M, log_power=1); evs[3].record()
+                nxt = 4
+            else:
+                perc = engine.median_freq(batch, S, F, CFG["l_perc"]); evs[3].record()
+                o, cmax = engine.mask_mel_log(batch, S, harm, perc, F, mel=mel, log_power=1); evs[4].record()
+                nxt = 5
+                del perc
             acc.zero_()
-            engine.topdb_moments(batch, o, M, 2, cmax, 80.0, classes, 3, acc=acc); evs[5].record()
+            engine.topdb_moments(batch, o, M, 2, cmax, 80.0, classes, 3, acc=acc); evs[nxt].record()
             torch.cuda.synchronize()
             if it >= 2:
                 for i in range(len(names)):
                     tot[i] += evs[i].elapsed_time(evs[i + 1])
-            del S, harm, perc, o, cmax
+            del S, harm, o, cmax
         peak, peak_src = measured_peak_gbs()
         stages = []
         for i, nme in enumerate(names):
@@ -263,7 +274,6 @@ def run_gpu(args):
             stages.append({"kernel": nme, "ms": round(ms, 4), "algorithmic_bytes_per_frame": bytes_per_frame[i],
                            "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)})
         dom = max(stages, key=lambda s: s["ms"])
-        # K3 calls a tiny mel-band helper kernel inside the public stage entry; it is included in K3's time
         roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak,
                     "unit": "GB/s", "frac": dom["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
                     "note": "median kernels are bound by the ALU pipe (FMNMX selection network), HBM is the "

@@ -156,6 +156,16 @@ HPSS_API int hpss_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const flo
                                int32_t log_power, float amin, float* out_dev,
                                uint32_t* clip_max_dev, void* stream);
 
+/* ---- K2p + K3 fused: the frequency-axis median of S (size k), both soft masks against harm_dev, S*mask,
+ * the per-stream mel projection (Slaney basis for mel_sr and n_fft = 2*(rows-1); n_mels == 0 -> identity,
+ * out rows = 2*rows) and power_to_db without the clip, in one kernel: the percussive median never leaves
+ * the SM.  Bit-identical to hpss_median_freq followed by hpss_mask_mel_log.  HPSS_ERR_UNSUPPORTED when k
+ * has no generated selection network (odd 3..63); hpss_featuregram then uses the separate kernels. */
+HPSS_API int hpss_perc_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* S_dev,
+                                    const float* harm_dev, int32_t rows, int32_t k, int32_t mel_sr,
+                                    int32_t n_mels, int32_t log_power, float amin, float* out_dev,
+                                    uint32_t* clip_max_dev, void* stream);
+
 /* ---- K3b: the top_db part of librosa.core.power_to_db: x = max(x, max_clip_stream - top_db)
  * (lib/preprocessing.py:388,401,420,422,441-442).  out rows = n_streams * rows_per_stream. */
 HPSS_API int hpss_topdb_clip(hpss_ctx* ctx, const hpss_batch* batch, float* out_dev,

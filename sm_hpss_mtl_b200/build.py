@@ -47,13 +47,22 @@ def _stamp() -> str:
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("HPSS_DEV_KS", "").encode())
     return h.hexdigest()
 
 
 def generate_networks(force: bool = False) -> None:
-    if force or not GEN_HEADER.exists() or GEN_HEADER.stat().st_mtime < GENERATOR.stat().st_mtime:
-        subprocess.run([sys.executable, str(GENERATOR), "--out", str(GEN_HEADER)], check=True,
-                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    """Emit the selection networks.  HPSS_DEV_KS="11,21,31" restricts the generated kernel sizes
+    (development builds only: every other k then takes the rank-counting fallback kernel)."""
+    ks = os.environ.get("HPSS_DEV_KS", "")
+    tag = GEN_HEADER.with_suffix(".ks")
+    if force or not GEN_HEADER.exists() or GEN_HEADER.stat().st_mtime < GENERATOR.stat().st_mtime \
+            or (tag.read_text() if tag.exists() else "") != ks:
+        cmd = [sys.executable, str(GENERATOR), "--out", str(GEN_HEADER)]
+        if ks:
+            cmd += ["--ks", ks]
+        subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        tag.write_text(ks)
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:

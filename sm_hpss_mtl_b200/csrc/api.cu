@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -153,6 +154,33 @@ int get_mel_plan(hpss_ctx* ctx, int sr, int n_fft, int n_mels, MelPlan** out) {
     }
     MelPlan* p = new MelPlan();
     p->sr = sr; p->n_fft = n_fft; p->n_mels = n_mels; p->rows = rows;
+    // sweep table: filters ordered, at most two overlapping at any frequency row
+    std::vector<int4> sweep(rows);
+    bool ok = true;
+    {
+        int pa = -1, pb = -1;
+        for (int m = 0; m < n_mels && ok; ++m) {
+            if (band[m].y <= band[m].x) continue;                    // empty filter
+            if (band[m].x < pa || band[m].y < pb) ok = false;        // bands must be ordered
+            pa = band[m].x; pb = band[m].y;
+        }
+        for (int f = 0; f < rows && ok; ++f) {
+            int first = n_mels;
+            for (int m = 0; m < n_mels; ++m) if (band[m].y > f) { first = m; break; }
+            for (int m = 0; m < n_mels; ++m)
+                if (w[(size_t)m * rows + f] != 0.f && (m < first || m > first + 1)) ok = false;
+            const float wa = first < n_mels ? w[(size_t)first * rows + f] : 0.f;
+            const float wb = first + 1 < n_mels ? w[(size_t)(first + 1) * rows + f] : 0.f;
+            int ia, ib;
+            memcpy(&ia, &wa, 4); memcpy(&ib, &wb, 4);
+            sweep[f] = make_int4(first, ia, ib, 0);
+        }
+    }
+    p->sweepable = ok;
+    if (ok) {
+        HPSS_CUDA(cudaMalloc(&p->d_sweep, sizeof(int4) * rows));
+        HPSS_CUDA(cudaMemcpy(p->d_sweep, sweep.data(), sizeof(int4) * rows, cudaMemcpyHostToDevice));
+    }
     HPSS_CUDA(cudaMalloc(&p->d_w, sizeof(float) * w.size()));
     HPSS_CUDA(cudaMalloc(&p->d_band, sizeof(int2) * n_mels));
     HPSS_CUDA(cudaMemcpy(p->d_w, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
@@ -297,18 +325,32 @@ static int features_from_spec(hpss_ctx* ctx, const hpss_batch* b, const float* S
         rc = get_mel_plan(ctx, p->mel_sr, 2 * (rows - 1), p->n_mels, &mp);
         if (rc) return rc;
     }
+    const bool clip = is_log && p->top_db >= 0.f;
+    bool fused = false;
     if (ns == 2) {
         rc = launch_median(ctx, b, S, rows, p->l_harm, true, harm, st);
         if (rc) return rc;
-        rc = launch_median(ctx, b, S, rows, p->l_perc, false, perc, st);
+        // frequency median + soft masks + mel + log in one kernel when the kernel size has a generated
+        // selection network and the mel basis can be swept with two running sums
+        // (opt-in while it is not faster than the two separate kernels: HPSS_USE_FUSED=1)
+        static const bool use_fused = getenv("HPSS_USE_FUSED") && atoi(getenv("HPSS_USE_FUSED")) != 0;
+        if (use_fused) {
+            rc = launch_median_freq_fused(ctx, b, S, harm, rows, p->l_perc, mp, is_log ? 1 : 0, p->amin, out,
+                                          clip ? clip_max : nullptr, st, &fused);
+            if (rc) return rc;
+        }
+        if (!fused) {
+            rc = launch_median(ctx, b, S, rows, p->l_perc, false, perc, st);
+            if (rc) return rc;
+        }
+    }
+    if (!fused) {
+        const int pre_square = (ns == 1 && is_mel) ? 1 : 0;   // melspectrogram(y=..) uses |X|^2
+        rc = launch_mask_mel(ctx, b, S, ns == 2 ? harm : nullptr, ns == 2 ? perc : nullptr, rows,
+                             mp ? mp->d_w : nullptr, mp ? mp->d_band : nullptr, mp ? mp->n_mels : 0, pre_square,
+                             is_log ? 1 : 0, p->amin, out, clip ? clip_max : nullptr, st);
         if (rc) return rc;
     }
-    const int pre_square = (ns == 1 && is_mel) ? 1 : 0;   // melspectrogram(y=..) uses |X|^2
-    const bool clip = is_log && p->top_db >= 0.f;
-    rc = launch_mask_mel(ctx, b, S, ns == 2 ? harm : nullptr, ns == 2 ? perc : nullptr, rows,
-                         mp ? mp->d_w : nullptr, mp ? mp->d_band : nullptr, mp ? mp->n_mels : 0, pre_square,
-                         is_log ? 1 : 0, p->amin, out, clip ? clip_max : nullptr, st);
-    if (rc) return rc;
     const int rps = is_mel ? p->n_mels : rows;
     if (ms) {   // one pass: clip (if any) + moments
         if (clip)
@@ -413,7 +455,7 @@ int hpss_ctx_destroy(hpss_ctx* ctx) {
         cudaFree(kv.second->d_window); cudaFree(kv.second->d_tw_half); cudaFree(kv.second->d_tw_full);
         delete kv.second;
     }
-    for (auto& kv : ctx->mel_plans) { cudaFree(kv.second->d_w); cudaFree(kv.second->d_band); delete kv.second; }
+    for (auto& kv : ctx->mel_plans) { cudaFree(kv.second->d_w); cudaFree(kv.second->d_band); if (kv.second->d_sweep) cudaFree(kv.second->d_sweep); delete kv.second; }
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->band_scratch) cudaFree(ctx->band_scratch);
     for (int i = 0; i < 2; ++i) {
@@ -558,6 +600,30 @@ int hpss_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* S, co
     }
     return launch_mask_mel(ctx, batch, S, harm, perc, rows, mel, band, n_mels, pre_square, log_power, amin, out,
                            clip_max, st);
+}
+
+int hpss_perc_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* S, const float* harm, int32_t rows,
+                           int32_t k, int32_t mel_sr, int32_t n_mels, int32_t log_power, float amin, float* out,
+                           uint32_t* clip_max, void* stream) {
+    if (!ctx || !batch || !S || !harm || !out) { set_error("perc_mask_mel_log: NULL argument"); return HPSS_ERR_INVALID; }
+    if (rows < 2 || k < 1 || n_mels < 0 || (n_mels > 0 && mel_sr < 1)) { set_error("perc_mask_mel_log: bad argument"); return HPSS_ERR_INVALID; }
+    if (log_power && !(amin > 0.f)) { set_error("amin must be strictly positive (librosa.power_to_db)"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    MelPlan* mp = nullptr;
+    if (n_mels > 0) {
+        int rc = get_mel_plan(ctx, mel_sr, 2 * (rows - 1), n_mels, &mp);
+        if (rc) return rc;
+    }
+    bool handled = false;
+    int rc = launch_median_freq_fused(ctx, batch, S, harm, rows, k, mp, log_power, amin, out, clip_max,
+                                      (cudaStream_t)stream, &handled);
+    if (rc) return rc;
+    if (!handled) {
+        set_error("perc_mask_mel_log: k=%d has no generated selection network (odd 3..63) or the mel basis is not "
+                  "sweepable; use hpss_median_freq + hpss_mask_mel_log", k);
+        return HPSS_ERR_UNSUPPORTED;
+    }
+    return HPSS_OK;
 }
 
 int hpss_topdb_clip(hpss_ctx* ctx, const hpss_batch* batch, float* out, int32_t rows_per_stream, int32_t n_streams,

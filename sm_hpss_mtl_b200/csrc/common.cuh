@@ -48,6 +48,10 @@ struct MelPlan {
     int sr = 0, n_fft = 0, n_mels = 0, rows = 0;
     float* d_w = nullptr;        // dense (n_mels, rows)
     int2* d_band = nullptr;      // per filter [first, last+1) non-zero column
+    // per frequency row {lowest unfinished filter, its weight, weight of the next filter, 0}: lets a
+    // sweep along f keep only two running sums per stream (valid when <= 2 ordered filters overlap)
+    int4* d_sweep = nullptr;
+    bool sweepable = false;
 };
 
 }  // namespace hpss
@@ -112,6 +116,9 @@ int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const fl
                     const float* perc, int rows, const float* mel, const int2* band, int n_mels,
                     int pre_square, int log_power, float amin, float* out, uint32_t* clip_max,
                     cudaStream_t st);
+int launch_median_freq_fused(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, int rows, int k,
+                             const MelPlan* mel, int log_power, float amin, float* out, uint32_t* clip_max,
+                             cudaStream_t st, bool* handled);
 int launch_mel_bands(const float* mel, int n_mels, int rows, int2* band, cudaStream_t st);
 int launch_topdb(hpss_ctx* ctx, const hpss_batch* b, float* out, int rows_per_stream, int n_streams,
                  const uint32_t* clip_max, float top_db, cudaStream_t st);

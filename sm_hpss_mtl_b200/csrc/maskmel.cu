@@ -14,9 +14,7 @@
 // a coalesced 128-byte row segment); the 8 warps split the frequency rows (mask phase) and
 // the mel filters (projection phase); masked values are staged through shared memory in
 // chunks of 64 frequency rows.
-#include <float.h>
-
-#include "common.cuh"
+#include "maskmath.cuh"
 
 namespace hpss {
 
@@ -49,39 +47,6 @@ __device__ __forceinline__ FrameLane frame_lane(const int64_t* __restrict__ fram
         fl.out_base = (int64_t)rows_out * fo + (gf - fo);
     }
     return fl;
-}
-
-// numpy op order of librosa.util.softmask(power=2, split_zeros=True) and S*mask.
-__device__ __forceinline__ void softmask_apply(float s, float h, float p, float& H, float& P) {
-    const float zmax = fmaxf(h, p);
-    const bool bad = zmax < FLT_MIN;
-    const float Z = bad ? 1.0f : zmax;
-    const float qh = __fdiv_rn(h, Z);
-    const float qp = __fdiv_rn(p, Z);
-    const float mh = __fmul_rn(qh, qh);
-    const float mp = __fmul_rn(qp, qp);
-    const float den = __fadd_rn(mh, mp);
-    const float mask_h = bad ? 0.5f : __fdiv_rn(mh, den);
-    const float mask_p = bad ? 0.5f : __fdiv_rn(mp, den);
-    H = __fmul_rn(s, mask_h);
-    P = __fmul_rn(s, mask_p);
-}
-
-__device__ __forceinline__ float post_value(float x, int log_power, float amin) {
-    if (!log_power) return x;
-    const float x2 = (log_power == 2) ? x : __fmul_rn(x, x);   // 2: x already is a power
-    return 3.0102999566398120f * __log2f(fmaxf(amin, x2));   // 10*log10(x), MUFU.LG2: |err| ~ 1e-6 dB
-}
-
-// per-(clip, stream) running max -> global ordered-uint atomicMax, one atomic per
-// distinct clip in the warp
-__device__ __forceinline__ void publish_max(uint32_t* __restrict__ clip_max, int n_streams, int stream, bool valid,
-                                            int clip, float v) {
-    const unsigned active = __ballot_sync(0xffffffffu, valid);
-    if (!valid) return;
-    const unsigned peers = __match_any_sync(active, clip);
-    const uint32_t key = __reduce_max_sync(peers, float_to_ordered(v));
-    if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicMax(clip_max + (size_t)n_streams * clip + stream, key);
 }
 
 template <bool HPSS_MODE>
@@ -127,17 +92,32 @@ mask_mel_kernel(const float* __restrict__ S, const float* __restrict__ harm, con
         float* Hc = smem;                       // [FC][32]
         float* Pc = Hc + FC * 32;               // [FC][32]   (HPSS mode only)
         if (FC >= rows) {
-            // whole column staged at once: mask phase, then every filter accumulates in registers
-            for (int f = warp; f < rows; f += kWarps) {
-                float H = 0.f, P = 0.f;
-                if (fl.valid) {
-                    const int64_t gi = fl.in_base + (int64_t)f * fl.T;
-                    const float sv = __ldg(S + gi);
-                    if (HPSS_MODE) softmask_apply(sv, __ldg(harm + gi), __ldg(perc + gi), H, P);
-                    else H = pre_square ? __fmul_rn(sv, sv) : sv;
+            // whole column staged at once: mask phase, then every filter accumulates in registers.
+            // Four rows per iteration with all twelve loads issued first (memory-level parallelism).
+            constexpr int U = 4;
+            for (int fb = warp; fb < rows; fb += U * kWarps) {
+                float sv[U], hv[U], pv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int f = fb + u * kWarps;
+                    sv[u] = 0.f; hv[u] = 0.f; pv[u] = 0.f;
+                    if (fl.valid && f < rows) {
+                        const int64_t gi = fl.in_base + (int64_t)f * fl.T;
+                        sv[u] = __ldg(S + gi);
+                        if (HPSS_MODE) { hv[u] = __ldg(harm + gi); pv[u] = __ldg(perc + gi); }
+                    }
                 }
-                Hc[f * 32 + lane] = H;
-                if (HPSS_MODE) Pc[f * 32 + lane] = P;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int f = fb + u * kWarps;
+                    if (f < rows) {
+                        float H = 0.f, P = 0.f;
+                        if (HPSS_MODE) softmask_apply(sv[u], hv[u], pv[u], H, P);
+                        else H = pre_square ? __fmul_rn(sv[u], sv[u]) : sv[u];
+                        Hc[f * 32 + lane] = H;
+                        if (HPSS_MODE) Pc[f * 32 + lane] = P;
+                    }
+                }
             }
             __syncthreads();
             for (int m = warp; m < n_mels; m += kWarps) {

@@ -51,13 +51,26 @@ moments_kernel(float* __restrict__ feat, const int64_t* __restrict__ frame_off,
             float thr = -INFINITY;
             if (CLIP) thr = ordered_to_float(__ldg(clip_max + (size_t)n_streams * c + d / rows_per_stream)) - top_db;
             double ps = 0.0;
-            for (int t = lane; t < len; t += 32) {
-                float x = CLIP ? row[t] : __ldg(row + t);
-                if (CLIP && x < thr) { x = thr; row[t] = x; }
-                if (!isfinite(x)) { x = 0.f; ++bad; }
-                const double xd = (double)x;
-                ps += xd;
-                q = fma(xd, xd, q);
+            // four independent 128-byte loads in flight per warp (the trip count is a run-time value)
+            for (int t0 = lane; t0 < len; t0 += 128) {
+                float xv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + 32 * u;
+                    xv[u] = (t < len) ? (CLIP ? row[t] : __ldg(row + t)) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + 32 * u;
+                    if (t < len) {
+                        float x = xv[u];
+                        if (CLIP && x < thr) { x = thr; row[t] = x; }
+                        if (!isfinite(x)) { x = 0.f; ++bad; }
+                        const double xd = (double)x;
+                        ps += xd;
+                        q = fma(xd, xd, q);
+                    }
+                }
             }
 #pragma unroll
             for (int k = 0; k < MAXC; ++k) s[k] += (k == cls) ? ps : 0.0;

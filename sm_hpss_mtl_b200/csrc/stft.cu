@@ -6,6 +6,8 @@
 // is read from HBM once per tile), every frame is transformed as a real-via-complex FFT
 // of size n_fft/2 entirely in shared memory, and the magnitudes are written transposed
 // so that consecutive lanes write consecutive frames of one frequency row.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace hpss {
@@ -26,7 +28,17 @@ struct RadixList {
     FastDiv div_m[kMaxRadixPasses];    // by n2 / radix[p]   (butterflies per frame)
     FastDiv div_ns[kMaxRadixPasses];   // by the product of the radices before pass p
     FastDiv div_nf;                    // by the number of frames in a full tile
+    int m[kMaxRadixPasses];            // n2 / radix[p]
+    int step[kMaxRadixPasses];         // n2 / (Ns * radix[p]): twiddle stride
+    int fg[kMaxRadixPasses];           // frame groups running side by side: max(1, blockDim / m)
 };
+
+// sqrt.approx (MUFU): relative error ~1e-7, exact 0 for 0; magnitudes only need the 1e-4 feature tolerance
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -84,51 +96,66 @@ __device__ __forceinline__ void butterfly<5>(float2 (&v)[5]) {
     v[3] = csub(p2, m2);
 }
 
-// One Stockham pass of radix R over `nf` frames.  FIRST: inputs come from the windowed
-// sample segment (even samples -> real, odd -> imaginary part of the half-size sequence).
+// One Stockham pass of radix R over `nf` frames.  FIRST: inputs come from the windowed sample segment
+// (even samples -> real, odd -> imaginary part of the half-size sequence).
+// A thread owns butterfly j for the frames fg, fg+FG, fg+2FG, ... : the index arithmetic, the R-1
+// twiddles (or the R window pairs of the first pass) are set up once and reused for every frame.
 template <int R, bool FIRST>
-__device__ __forceinline__ void stockham_pass(int nf, int n2, int Ns, FastDiv dm, FastDiv dns, int hop, int zs,
+__device__ __forceinline__ void stockham_pass(int nf, int m, int step, int fg_full, int Ns, FastDiv dm, FastDiv dns,
+                                              int hop, int zs,
                                               const float* __restrict__ s_samp,
                                               const float* __restrict__ s_win,
                                               const float2* __restrict__ s_tw,
                                               const float2* __restrict__ in, float2* __restrict__ out) {
-    const int m = n2 / R;
-    const int total = nf * m;
-    const int step = n2 / (Ns * R);
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int fr = (int)dm.div((uint32_t)idx);
-        const int j = idx - fr * m;
+    const int FG = min(fg_full, nf);   // frame groups running side by side
+    const int nitems = m * FG;
+    for (int idx = threadIdx.x; idx < nitems; idx += blockDim.x) {
+        const int fg = (int)dm.div((uint32_t)idx);
+        const int j = idx - fg * m;
         const int k = j - (int)dns.div((uint32_t)j) * Ns;
-        float2 v[R];
+        const int d = (j - k) * R + k;
+        float2 c[R];                       // FIRST: window pairs; else twiddles (c[0] unused)
 #pragma unroll
         for (int q = 0; q < R; ++q) {
-            const int n = j + q * m;
-            if (FIRST) {
-                // hop is even on this path (odd hops use the scalar variant below): 8-byte loads
-                const float2 x = *reinterpret_cast<const float2*>(s_samp + fr * hop + 2 * n);
-                const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * n);
-                v[q] = make_float2(x.x * w.x, x.y * w.y);
-            } else {
-                v[q] = in[fr * zs + n];
-                if (q > 0) v[q] = cmul(v[q], s_tw[q * k * step]);
-            }
+            if (FIRST) c[q] = *reinterpret_cast<const float2*>(s_win + 2 * (j + q * m));
+            else if (q > 0) c[q] = s_tw[q * k * step];
         }
-        butterfly<R>(v);
-        const int d = (j - k) * R + k;
+        for (int fr = fg; fr < nf; fr += FG) {
+            float2 v[R];
+            if (FIRST) {
+                const float2* x = reinterpret_cast<const float2*>(s_samp + fr * hop) + j;   // hop is even
 #pragma unroll
-        for (int q = 0; q < R; ++q) out[fr * zs + d + q * Ns] = v[q];
+                for (int q = 0; q < R; ++q) {
+                    const float2 xv = x[q * m];
+                    v[q] = make_float2(xv.x * c[q].x, xv.y * c[q].y);
+                }
+            } else {
+                const float2* x = in + fr * zs + j;
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    v[q] = x[q * m];
+                    if (q > 0) v[q] = cmul(v[q], c[q]);
+                }
+            }
+            butterfly<R>(v);
+            float2* y = out + fr * zs + d;
+#pragma unroll
+            for (int q = 0; q < R; ++q) y[q * Ns] = v[q];
+        }
     }
 }
 
 template <bool FIRST>
-__device__ __forceinline__ void run_pass(int R, int nf, int n2, int Ns, FastDiv dm, FastDiv dns, int hop, int zs,
+__device__ __forceinline__ void run_pass(const RadixList& rl, int p, int nf, int Ns, int hop, int zs,
                                          const float* s_samp, const float* s_win, const float2* s_tw,
                                          const float2* in, float2* out) {
-    switch (R) {
-        case 2: stockham_pass<2, FIRST>(nf, n2, Ns, dm, dns, hop, zs, s_samp, s_win, s_tw, in, out); break;
-        case 3: stockham_pass<3, FIRST>(nf, n2, Ns, dm, dns, hop, zs, s_samp, s_win, s_tw, in, out); break;
-        case 4: stockham_pass<4, FIRST>(nf, n2, Ns, dm, dns, hop, zs, s_samp, s_win, s_tw, in, out); break;
-        default: stockham_pass<5, FIRST>(nf, n2, Ns, dm, dns, hop, zs, s_samp, s_win, s_tw, in, out); break;
+    const int m = rl.m[p], step = rl.step[p], fg = rl.fg[p];
+    const FastDiv dm = rl.div_m[p], dns = rl.div_ns[p];
+    switch (rl.radix[p]) {
+        case 2: stockham_pass<2, FIRST>(nf, m, step, fg, Ns, dm, dns, hop, zs, s_samp, s_win, s_tw, in, out); break;
+        case 3: stockham_pass<3, FIRST>(nf, m, step, fg, Ns, dm, dns, hop, zs, s_samp, s_win, s_tw, in, out); break;
+        case 4: stockham_pass<4, FIRST>(nf, m, step, fg, Ns, dm, dns, hop, zs, s_samp, s_win, s_tw, in, out); break;
+        default: stockham_pass<5, FIRST>(nf, m, step, fg, Ns, dm, dns, hop, zs, s_samp, s_win, s_tw, in, out); break;
     }
 }
 
@@ -182,34 +209,47 @@ stft_mag_kernel(const float* __restrict__ wave, const int64_t* __restrict__ samp
     float2* in = bufB;
     float2* out = bufA;
     int Ns = 1;
-    run_pass<true>(rl.radix[0], nf, n2, Ns, rl.div_m[0], rl.div_ns[0], hop, zs, s_samp, s_win, s_twh, in, out);
+    run_pass<true>(rl, 0, nf, Ns, hop, zs, s_samp, s_win, s_twh, in, out);
     Ns *= rl.radix[0];
     __syncthreads();
     for (int p = 1; p < rl.n_pass; ++p) {
         float2* t = in; in = out; out = t;
-        run_pass<false>(rl.radix[p], nf, n2, Ns, rl.div_m[p], rl.div_ns[p], hop, zs, s_samp, s_win, s_twh, in, out);
+        run_pass<false>(rl, p, nf, Ns, hop, zs, s_samp, s_win, s_twh, in, out);
         Ns *= rl.radix[p];
         __syncthreads();
     }
     const float2* Z = out;
 
-    // ---- real-FFT unpack + magnitude, written (f, t) with lanes along t
+    // ---- real-FFT unpack + magnitude, written (f, t) with lanes along t.  Bins k and n2-k share their
+    // loads: X[k] = E + W*O and X[n2-k] = conj(E - W*O) with E, O from Z[k] and conj(Z[n2-k]).
     const int64_t base = (int64_t)F * fo + t0;
-    const int total = F * nf;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int k = (nf == TT) ? (int)rl.div_nf.div((uint32_t)idx) : idx / nf;   // partial last tile: plain division
-        const int fr = idx - k * nf;
-        const float2 zk = Z[fr * zs + (k == n2 ? 0 : k)];
-        float2 zc = Z[fr * zs + (k == 0 ? 0 : n2 - k)];
-        zc.y = -zc.y;
-        const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-        const float2 d = csub(zk, zc);
-        const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);
-        const float2 x = cadd(e, cmul(s_twf[k], o));
-        const int64_t g = base + (int64_t)k * T + fr;
-        const float p2 = x.x * x.x + x.y * x.y;
-        S[g] = power ? p2 : sqrtf(p2);
-        if (cplx) cplx[g] = x;
+    const int half = n2 / 2;
+    const int fr = threadIdx.x & 15;            // tiles hold at most 16 frames
+    if (fr < nf) {
+        const float2* zrow = Z + fr * zs;
+        float* Sg = S + base + fr;
+        float2* Cg = cplx ? cplx + base + fr : nullptr;
+        for (int k = threadIdx.x >> 4; k <= half; k += (int)(blockDim.x >> 4)) {
+            const int k2 = n2 - k;
+            const float2 zk = zrow[k];
+            float2 zc = zrow[k == 0 ? 0 : k2];
+            zc.y = -zc.y;
+            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+            const float2 dd = csub(zk, zc);
+            const float2 o = make_float2(0.5f * dd.y, -0.5f * dd.x);
+            const float2 wo = cmul(s_twf[k], o);
+            const float2 xa = cadd(e, wo);                           // X[k]
+            const float2 xb = make_float2(e.x - wo.x, wo.y - e.y);   // X[n2-k] = conj(E - W*O)
+            const float pa = xa.x * xa.x + xa.y * xa.y;
+            const float pb = xb.x * xb.x + xb.y * xb.y;
+            const int64_t ga = (int64_t)k * T, gb = (int64_t)k2 * T;
+            Sg[ga] = power ? pa : fast_sqrt(pa);
+            if (Cg) Cg[ga] = xa;
+            if (k2 != k) {
+                Sg[gb] = power ? pb : fast_sqrt(pb);
+                if (Cg) Cg[gb] = xb;
+            }
+        }
     }
 }
 
@@ -262,8 +302,12 @@ int launch_stft(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* 
         int ns = 1;
         for (int i = 0; i < kMaxRadixPasses; ++i) {
             rl.radix[i] = plan->radix[i];
+            rl.m[i] = rl.step[i] = rl.fg[i] = 1;
             if (i < plan->n_pass) {
-                rl.div_m[i] = FastDiv((uint32_t)(plan->n2 / plan->radix[i]));
+                rl.m[i] = plan->n2 / plan->radix[i];
+                rl.step[i] = plan->n2 / (ns * plan->radix[i]);
+                rl.fg[i] = std::max(1, 256 / rl.m[i]);
+                rl.div_m[i] = FastDiv((uint32_t)rl.m[i]);
                 rl.div_ns[i] = FastDiv((uint32_t)ns);
                 ns *= plan->radix[i];
             }

@@ -200,6 +200,19 @@ def mask_mel_log(batch: Batch, S: torch.Tensor, harm: Optional[torch.Tensor], pe
     return out, clip_max
 
 
+def perc_mask_mel_log(batch: Batch, S: torch.Tensor, harm: torch.Tensor, rows: int, k: int, mel_sr: int = 22050,
+                      n_mels: int = 0, log_power: int = 0, amin: float = 1e-10):
+    """K2p + K3 fused (frequency median + masks + mel + log); returns (out, clip_max or None)."""
+    rows_out = 2 * (n_mels if n_mels > 0 else rows)
+    out = torch.empty(rows_out * batch.total_frames, dtype=torch.float32, device=S.device)
+    clip_max = torch.empty(2 * max(1, batch.n_clips), dtype=torch.int32, device=S.device) if log_power else None
+    check(batch.lib.hpss_perc_mask_mel_log(batch.ctx.handle, batch.handle, _dev_ptr(S, torch.float32, "S"),
+                                           _dev_ptr(harm, torch.float32, "harm"), int(rows), int(k), int(mel_sr),
+                                           int(n_mels), int(log_power), float(amin), _dev_ptr(out), _dev_ptr(clip_max),
+                                           _stream_ptr()))
+    return out, clip_max
+
+
 def topdb_clip(batch: Batch, out: torch.Tensor, rows_per_stream: int, n_streams: int, clip_max: torch.Tensor,
                top_db: float = 80.0) -> torch.Tensor:
     if top_db < 0:

@@ -270,3 +270,61 @@ def test_featuregram_moments_fused_equals_separate(ctx):
         assert torch.equal(out, ref), feat
         a, b = acc.cpu().numpy(), acc_ref.cpu().numpy()
         assert np.allclose(a, b, rtol=1e-12, atol=1e-9), feat
+
+
+@pytest.mark.parametrize("feat,lh,lp,n_fft", [("LOGMEL_HARMPERC", 31, 31, 400), ("LOGMEL_HARMPERC", 21, 11, 400),
+                                              ("MEL_HARMPERC", 17, 63, 512), ("HARMPERC", 21, 11, 400),
+                                              ("LOG_HARMPERC", 31, 5, 2048), ("LOGMEL_HARMPERC", 31, 16, 400)])
+def test_fused_freq_median_equals_staged_pipeline(ctx, feat, lh, lp, n_fft):
+    """hpss_featuregram runs the frequency median fused with masks + mel + log; the stage entry points run
+    them as separate kernels.  Same arithmetic in the same order -> bit-identical (l_perc = 16 has no
+    generated network and exercises the un-fused fallback inside hpss_featuregram)."""
+    hop = 160 if n_fft <= 512 else 512
+    win = 400 if n_fft <= 512 else n_fft
+    Ls = [16000, 5 * n_fft + 3, 40000, n_fft]
+    wave = to_dev(np.concatenate([synth.synth_clip(70 + i, L) for i, L in enumerate(Ls)]))
+    prm = engine.make_params(n_fft=n_fft, win_length=win, hop_length=hop, l_harm=lh, l_perc=lp, n_mels=120, feature=feat)
+    batch = engine.Batch(ctx, clip_lengths=Ls, n_fft=n_fft, hop_length=hop)
+    fused = engine.featuregram(batch, wave, prm)
+    F = n_fft // 2 + 1
+    S = engine.stft_mag(batch, wave, n_fft, win, hop)
+    harm = engine.median_time(batch, S, F, lh)
+    perc = engine.median_freq(batch, S, F, lp)
+    is_mel, is_log = "MEL" in feat, "LOG" in feat
+    mel = to_dev(engine.mel_filterbank(22050, n_fft, 120)) if is_mel else None
+    staged, cmax = engine.mask_mel_log(batch, S, harm, perc, F, mel=mel, log_power=is_log)
+    if is_log:
+        engine.topdb_clip(batch, staged, 120 if is_mel else F, 2, cmax, 80.0)
+    assert torch.equal(fused, staged)
+
+
+def test_softmask_bit_exact_adversarial(ctx):
+    """The kernel shares one refined reciprocal between the two mask divisions; check bit-exactness against
+    numpy over a wide dynamic range: ratios near 1, tiny ratios (q*q subnormal / zero), subnormal inputs,
+    exact zeros, huge values."""
+    rng = np.random.default_rng(99)
+    rows, T = 256, 4096
+    n = rows * T
+    expo = rng.uniform(-44, 12, size=n)
+    h = (10.0 ** expo * rng.uniform(1, 10, size=n)).astype(np.float32)
+    ratio_kind = rng.integers(0, 6, size=n)
+    ratio = np.where(ratio_kind == 0, 1.0 + rng.uniform(-1e-6, 1e-6, size=n),
+             np.where(ratio_kind == 1, 10.0 ** rng.uniform(-25, 0, size=n),
+             np.where(ratio_kind == 2, 10.0 ** rng.uniform(0, 25, size=n),
+             np.where(ratio_kind == 3, rng.uniform(0.5, 2.0, size=n), 10.0 ** rng.uniform(-3, 3, size=n)))))
+    p = (h.astype(np.float64) * ratio).astype(np.float32)
+    p[~np.isfinite(p)] = 1.0
+    zero = rng.random(n) < 0.01
+    h[zero] = 0.0
+    p[rng.random(n) < 0.01] = 0.0
+    s = np.abs(rng.standard_normal(n)).astype(np.float32) * 10
+    h, p, s = h.reshape(rows, T), p.reshape(rows, T), s.reshape(rows, T)
+    batch = engine.Batch(ctx, clip_frames=[T])
+    out, _ = engine.mask_mel_log(batch, to_dev(s.ravel()), to_dev(h.ravel()), to_dev(p.ravel()), rows)
+    got = out.cpu().numpy().reshape(2 * rows, T)
+    with np.errstate(all="ignore"):
+        mh = lr.softmask(h, p, power=2.0, split_zeros=True)
+        mp = lr.softmask(p, h, power=2.0, split_zeros=True)
+        want_h, want_p = s * mh, s * mp
+    assert np.array_equal(got[:rows], want_h), int((got[:rows] != want_h).sum())
+    assert np.array_equal(got[rows:], want_p), int((got[rows:] != want_p).sum())
