@@ -243,7 +243,6 @@ def run_gpu(args):
         else:
             names = ["K1 stft_mag", "K2h median_time", "K2p median_freq", "K3 mask_mel_log", "K3b+K5 topdb_moments"]
             bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F, 12 * F + 8 * M, 16 * M]
-            mel = torch.from_numpy(engine.mel_filterbank(22050, CFG["n_fft"], M)).cuda()
         tot = [0.0] * len(names)
         reps = max(args.steps, 5)
         for it in range(reps + 2):
@@ -256,7 +255,7 @@ def run_gpu(args):
                 nxt = 4
             else:
                 perc = engine.median_freq(batch, S, F, CFG["l_perc"]); evs[3].record()
-                o, cmax = engine.mask_mel_log(batch, S, harm, perc, F, mel=mel, log_power=1); evs[4].record()
+                o, cmax = engine.mask_mel_log(batch, S, harm, perc, F, mel_sr=22050, n_mels=M, log_power=1); evs[4].record()
                 nxt = 5
                 del perc
             acc.zero_()

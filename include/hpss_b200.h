@@ -156,6 +156,16 @@ HPSS_API int hpss_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const flo
                                int32_t log_power, float amin, float* out_dev,
                                uint32_t* clip_max_dev, void* stream);
 
+/* Same with the basis librosa.feature.melspectrogram itself would build: the cached Slaney filterbank for
+ * (mel_sr, n_fft = 2*(rows-1), n_mels) (lib/preprocessing.py:409-410, 419, 421 -> sr = 22050; :394, :400 ->
+ * sr = 16000).  Lets the library use its banded single-sweep kernel; bit-identical to hpss_mask_mel_log
+ * called with hpss_mel_filterbank(mel_sr, 2*(rows-1), n_mels). */
+HPSS_API int hpss_mask_mel_log_sr(hpss_ctx* ctx, const hpss_batch* batch, const float* S_dev,
+                                  const float* harm_dev, const float* perc_dev, int32_t rows,
+                                  int32_t mel_sr, int32_t n_mels, int32_t pre_square,
+                                  int32_t log_power, float amin, float* out_dev,
+                                  uint32_t* clip_max_dev, void* stream);
+
 /* ---- K2p + K3 fused: the frequency-axis median of S (size k), both soft masks against harm_dev, S*mask,
  * the per-stream mel projection (Slaney basis for mel_sr and n_fft = 2*(rows-1); n_mels == 0 -> identity,
  * out rows = 2*rows) and power_to_db without the clip, in one kernel: the percussive median never leaves

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "hpss_median_time": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "hpss_median_freq": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "hpss_mask_mel_log": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
+    "hpss_mask_mel_log_sr": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
     "hpss_perc_mask_mel_log": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
     "hpss_topdb_clip": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp]),
     "hpss_feature_rows": (_i32, [C.POINTER(Params)]),

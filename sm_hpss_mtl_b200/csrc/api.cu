@@ -347,7 +347,9 @@ static int features_from_spec(hpss_ctx* ctx, const hpss_batch* b, const float* S
     if (!fused) {
         const int pre_square = (ns == 1 && is_mel) ? 1 : 0;   // melspectrogram(y=..) uses |X|^2
         rc = launch_mask_mel(ctx, b, S, ns == 2 ? harm : nullptr, ns == 2 ? perc : nullptr, rows,
-                             mp ? mp->d_w : nullptr, mp ? mp->d_band : nullptr, mp ? mp->n_mels : 0, pre_square,
+                             mp ? mp->d_w : nullptr, mp ? mp->d_band : nullptr,
+                             (mp && mp->sweepable && !getenv("HPSS_NO_SWEEP")) ? mp->d_sweep : nullptr,
+                             mp ? mp->n_mels : 0, pre_square,
                              is_log ? 1 : 0, p->amin, out, clip ? clip_max : nullptr, st);
         if (rc) return rc;
     }
@@ -598,8 +600,23 @@ int hpss_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* S, co
         int rc = launch_mel_bands(mel, n_mels, rows, band, st);
         if (rc) return rc;
     }
-    return launch_mask_mel(ctx, batch, S, harm, perc, rows, mel, band, n_mels, pre_square, log_power, amin, out,
-                           clip_max, st);
+    return launch_mask_mel(ctx, batch, S, harm, perc, rows, mel, band, nullptr, n_mels, pre_square, log_power, amin,
+                           out, clip_max, st);
+}
+
+int hpss_mask_mel_log_sr(hpss_ctx* ctx, const hpss_batch* batch, const float* S, const float* harm, const float* perc,
+                         int32_t rows, int32_t mel_sr, int32_t n_mels, int32_t pre_square, int32_t log_power,
+                         float amin, float* out, uint32_t* clip_max, void* stream) {
+    if (!ctx || !batch || !S || !out) { set_error("mask_mel_log_sr: NULL argument"); return HPSS_ERR_INVALID; }
+    if ((harm == nullptr) != (perc == nullptr)) { set_error("mask_mel_log_sr: harm and perc must both be given or both NULL"); return HPSS_ERR_INVALID; }
+    if (rows < 2 || n_mels < 1 || mel_sr < 1) { set_error("mask_mel_log_sr: rows=%d n_mels=%d mel_sr=%d", rows, n_mels, mel_sr); return HPSS_ERR_INVALID; }
+    if (log_power && !(amin > 0.f)) { set_error("amin must be strictly positive (librosa.power_to_db)"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    MelPlan* mp = nullptr;
+    int rc = get_mel_plan(ctx, mel_sr, 2 * (rows - 1), n_mels, &mp);
+    if (rc) return rc;
+    return launch_mask_mel(ctx, batch, S, harm, perc, rows, mp->d_w, mp->d_band, mp->sweepable ? mp->d_sweep : nullptr,
+                           n_mels, pre_square, log_power, amin, out, clip_max, (cudaStream_t)stream);
 }
 
 int hpss_perc_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* S, const float* harm, int32_t rows,

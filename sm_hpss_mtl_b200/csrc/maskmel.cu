@@ -198,6 +198,87 @@ mask_mel_kernel(const float* __restrict__ S, const float* __restrict__ harm, con
     }
 }
 
+// Sweep formulation of the HPSS mel features (the default whenever the basis is "sweepable": bands ordered,
+// at most two filters overlapping at any frequency row -- true for every Slaney basis the reference builds).
+// One warp owns 32 consecutive frames of the batch (lane = frame) and walks f = 0 .. rows-1 once: the three
+// loads per row are coalesced 128-byte segments, U rows are in flight at a time, the masked values go
+// straight into the two running sums per stream of the filters currently open and a finished filter is
+// emitted (square, log, store, running max) when f passes its upper edge.  No shared memory, no CTA
+// barrier, fully independent warps: occupancy (not a tile ring) hides the HBM latency.  Accumulation order
+// (f ascending, fmaf) is the one of mask_mel_kernel's whole-column path, so both give the same bits.
+template <int U>
+__global__ void __launch_bounds__(kThreads)
+mask_mel_sweep_kernel(const float* __restrict__ S, const float* __restrict__ harm, const float* __restrict__ perc,
+                      const int64_t* __restrict__ frame_off, const int32_t* __restrict__ block_clip,
+                      int64_t total_frames, int rows, const int4* __restrict__ sweep, int n_mels, int log_power,
+                      float amin, float* __restrict__ out, uint32_t* __restrict__ clip_max) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t g0 = ((int64_t)blockIdx.x * kWarps + warp) * 32;
+    if (g0 >= total_frames) return;
+    const FrameLane fl = frame_lane(frame_off, block_clip, total_frames, g0 + lane, rows, 2 * n_mels);
+    const int64_t T = fl.T;
+    const float* sp = S + fl.in_base;
+    const float* hp = harm + fl.in_base;
+    const float* pp = perc + fl.in_base;
+    float* oh = out + fl.out_base;
+    float* op = oh + (int64_t)n_mels * T;
+    float aH = 0.f, aP = 0.f, bH = 0.f, bP = 0.f;     // running sums of filters cur, cur + 1
+    float vmaxH = -INFINITY, vmaxP = -INFINITY;
+    int cur = 0;
+
+    auto emit = [&]() {
+        const float vH = post_value(aH, log_power, amin);
+        const float vP = post_value(aP, log_power, amin);
+        if (fl.valid) { *oh = vH; *op = vP; }
+        oh += T; op += T;
+        vmaxH = fmaxf(vmaxH, vH);
+        vmaxP = fmaxf(vmaxP, vP);
+        aH = bH; aP = bP; bH = 0.f; bP = 0.f;
+        ++cur;
+    };
+    auto row = [&](int f, float sv, float hv, float pv) {
+        float H, P;
+        softmask_apply(sv, hv, pv, H, P);
+        const int4 e = __ldg(sweep + f);
+#pragma unroll 1
+        while (cur < e.x) emit();                      // warp-uniform: the table does not depend on the lane
+        const float wA = __int_as_float(e.y), wB = __int_as_float(e.z);
+        aH = fmaf(wA, H, aH);
+        aP = fmaf(wA, P, aP);
+        bH = fmaf(wB, H, bH);
+        bP = fmaf(wB, P, bP);
+    };
+
+    int f0 = 0;
+    for (; f0 + U <= rows; f0 += U) {
+        float sv[U], hv[U], pv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            sv[u] = 0.f; hv[u] = 0.f; pv[u] = 0.f;
+            if (fl.valid) {
+                sv[u] = __ldg(sp + u * T);
+                hv[u] = __ldg(hp + u * T);
+                pv[u] = __ldg(pp + u * T);
+            }
+        }
+        sp += U * T; hp += U * T; pp += U * T;
+#pragma unroll
+        for (int u = 0; u < U; ++u) row(f0 + u, sv[u], hv[u], pv[u]);
+    }
+    for (; f0 < rows; ++f0) {
+        float sv = 0.f, hv = 0.f, pv = 0.f;
+        if (fl.valid) { sv = __ldg(sp); hv = __ldg(hp); pv = __ldg(pp); }
+        sp += T; hp += T; pp += T;
+        row(f0, sv, hv, pv);
+    }
+#pragma unroll 1
+    while (cur < n_mels) emit();                       // filters above the last frequency row
+    if (clip_max != nullptr) {
+        publish_max(clip_max, 2, 0, fl.valid, fl.clip, vmaxH);
+        publish_max(clip_max, 2, 1, fl.valid, fl.clip, vmaxP);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 topdb_kernel(float* __restrict__ out, const int64_t* __restrict__ frame_off, const int32_t* __restrict__ block_clip, int64_t total_frames,
              int rows_per_stream, int n_streams, const uint32_t* __restrict__ clip_max, float top_db) {
@@ -237,13 +318,21 @@ int launch_mel_bands(const float* mel, int n_mels, int rows, int2* band, cudaStr
 }
 
 int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, const float* perc,
-                    int rows, const float* mel, const int2* band, int n_mels, int pre_square, int log_power,
-                    float amin, float* out, uint32_t* clip_max, cudaStream_t st) {
+                    int rows, const float* mel, const int2* band, const int4* sweep, int n_mels, int pre_square,
+                    int log_power, float amin, float* out, uint32_t* clip_max, cudaStream_t st) {
     const int64_t total = b->frame_off[b->n_clips];
     const bool hpss_mode = harm != nullptr;
     const int ns = hpss_mode ? 2 : 1;
     if (clip_max) HPSS_CUDA(cudaMemsetAsync(clip_max, 0, sizeof(uint32_t) * (size_t)ns * b->n_clips, st));
     if (total == 0) return HPSS_OK;
+    if (hpss_mode && mel && sweep) {
+        const int64_t n_warps = (total + 31) / 32;
+        const unsigned grid = (unsigned)((n_warps + kWarps - 1) / kWarps);
+        mask_mel_sweep_kernel<4><<<grid, kThreads, 0, st>>>(S, harm, perc, b->d_frame_off, b->d_block_clip, total, rows,
+                                                            sweep, n_mels, log_power, amin, out, clip_max);
+        HPSS_LAUNCHED("mask_mel_sweep_kernel");
+        return HPSS_OK;
+    }
     size_t smem = 0;
     int FC = 0;
     if (mel) {

@@ -183,15 +183,24 @@ def median_freq(batch: Batch, S: torch.Tensor, rows: int, k: int) -> torch.Tenso
 
 def mask_mel_log(batch: Batch, S: torch.Tensor, harm: Optional[torch.Tensor], perc: Optional[torch.Tensor], rows: int,
                  mel: Optional[torch.Tensor] = None, pre_square: bool = False, log_power: bool = False,
-                 amin: float = 1e-10):
-    """Returns (out, clip_max): out rows = streams * (n_mels or rows); clip_max (uint32-coded) or None."""
+                 amin: float = 1e-10, mel_sr: Optional[int] = None, n_mels: int = 0):
+    """Returns (out, clip_max): out rows = streams * (n_mels or rows); clip_max (uint32-coded) or None.
+    The basis is either an explicit dense ``mel`` (n_mels, rows) tensor or, with ``mel_sr`` and ``n_mels``,
+    the library's cached Slaney filterbank for that sample rate (what melspectrogram itself builds)."""
     ns = 2 if harm is not None else 1
+    clip_max = torch.empty(ns * max(1, batch.n_clips), dtype=torch.int32, device=S.device) if log_power else None
+    if mel is None and mel_sr is not None and n_mels > 0:
+        out = torch.empty(ns * n_mels * batch.total_frames, dtype=torch.float32, device=S.device)
+        check(batch.lib.hpss_mask_mel_log_sr(batch.ctx.handle, batch.handle, _dev_ptr(S, torch.float32, "S"),
+                                             _dev_ptr(harm, torch.float32, "harm"), _dev_ptr(perc, torch.float32, "perc"),
+                                             int(rows), int(mel_sr), int(n_mels), int(bool(pre_square)), int(log_power),
+                                             float(amin), _dev_ptr(out), _dev_ptr(clip_max), _stream_ptr()))
+        return out, clip_max
     n_mels = 0 if mel is None else int(mel.shape[0])
     if mel is not None and tuple(mel.shape) != (n_mels, rows):
         raise ValueError(f"mel must be (n_mels, {rows})")
     rows_out = ns * (n_mels if mel is not None else rows)
     out = torch.empty(rows_out * batch.total_frames, dtype=torch.float32, device=S.device)
-    clip_max = torch.empty(ns * max(1, batch.n_clips), dtype=torch.int32, device=S.device) if log_power else None
     check(batch.lib.hpss_mask_mel_log(batch.ctx.handle, batch.handle, _dev_ptr(S, torch.float32, "S"),
                                       _dev_ptr(harm, torch.float32, "harm"), _dev_ptr(perc, torch.float32, "perc"),
                                       int(rows), _dev_ptr(mel, torch.float32, "mel"), n_mels, int(bool(pre_square)),

@@ -328,3 +328,29 @@ def test_softmask_bit_exact_adversarial(ctx):
         want_h, want_p = s * mh, s * mp
     assert np.array_equal(got[:rows], want_h), int((got[:rows] != want_h).sum())
     assert np.array_equal(got[rows:], want_p), int((got[rows:] != want_p).sum())
+
+
+@pytest.mark.parametrize("n_fft,sr,n_mels,Ts", [(400, 22050, 120, [98, 7, 300, 33]), (400, 16000, 21, [64]),
+                                                (512, 22050, 120, [50, 50]), (2048, 22050, 128, [40, 9])])
+def test_mask_mel_sweep_equals_dense_basis(ctx, n_fft, sr, n_mels, Ts):
+    """hpss_mask_mel_log_sr (single-sweep kernel on the cached Slaney basis) against hpss_mask_mel_log with the
+    same basis passed as a dense matrix: identical bits while the dense kernel stages whole columns (same
+    f-ascending fmaf order), 1e-6 relative L2 where it accumulates in 64-row chunks (n_fft = 2048)."""
+    rng = np.random.default_rng(n_fft + n_mels)
+    F = n_fft // 2 + 1
+    mats = [np.abs(rng.standard_normal((F, T))).astype(np.float32) * np.float32(10.0) ** rng.integers(-6, 3, (F, 1)).astype(np.float32)
+            for T in Ts]
+    batch = engine.Batch(ctx, clip_frames=Ts)
+    S = to_dev(flat_batch(mats))
+    harm = engine.median_time(batch, S, F, 17)
+    perc = engine.median_freq(batch, S, F, 17)
+    mel = to_dev(engine.mel_filterbank(sr, n_fft, n_mels))
+    for log_power in (False, True):
+        dense, cm_d = engine.mask_mel_log(batch, S, harm, perc, F, mel=mel, log_power=log_power)
+        sweep, cm_s = engine.mask_mel_log(batch, S, harm, perc, F, mel_sr=sr, n_mels=n_mels, log_power=log_power)
+        if F <= 264:
+            assert torch.equal(dense, sweep)
+            if log_power:
+                assert torch.equal(cm_d, cm_s)
+        else:
+            assert rel_l2(sweep.cpu().numpy(), dense.cpu().numpy()) < 1e-6

@@ -27,7 +27,7 @@ for it in range(reps + 2):
     o, cm = engine.perc_mask_mel_log(batch, S, harm, 201, k, 22050, 120, log_power=1); ev[3].record()
     engine.topdb_moments(batch, o, 120, 2, cm, 80.0, cls, 3, acc=acc); ev[4].record()
     perc = engine.median_freq(batch, S, 201, k); ev[5].record()
-    o2, cm2 = engine.mask_mel_log(batch, S, harm, perc, 201, mel=mel, log_power=1); ev[6].record()
+    o2, cm2 = engine.mask_mel_log(batch, S, harm, perc, 201, mel_sr=22050, n_mels=120, log_power=1); ev[6].record()
     torch.cuda.synchronize()
     if it >= 2:
         for i in range(6):
