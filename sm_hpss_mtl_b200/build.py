@@ -19,9 +19,11 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libhpss_b200.so"
 OBJ = PKG / "_build"
-SOURCES = ["api.cu", "stft.cu", "median.cu", "maskmel.cu", "stats.cu"]
+SOURCES = ["api.cu", "stft.cu", "stft_fast.cu", "median.cu", "maskmel.cu", "stats.cu"]
 GEN_HEADER = CSRC / "median_networks_gen.cuh"
 GENERATOR = ROOT / "tools" / "gen_median_networks.py"
+FFT_HEADER = CSRC / "fft_codelets_gen.cuh"
+FFT_GENERATOR = ROOT / "tools" / "gen_fft_codelets.py"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -41,8 +43,8 @@ def _nvcc() -> str:
 def _stamp() -> str:
     h = hashlib.sha256()
     for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "hpss_b200.h",
-                                                                          GENERATOR, Path(__file__)]):
-        if p.name == GEN_HEADER.name:
+                                                                          GENERATOR, FFT_GENERATOR, Path(__file__)]):
+        if p.name in (GEN_HEADER.name, FFT_HEADER.name):
             continue
         h.update(p.name.encode())
         h.update(p.read_bytes())
@@ -63,6 +65,9 @@ def generate_networks(force: bool = False) -> None:
             cmd += ["--ks", ks]
         subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         tag.write_text(ks)
+    if force or not FFT_HEADER.exists() or FFT_HEADER.stat().st_mtime < FFT_GENERATOR.stat().st_mtime:
+        subprocess.run([sys.executable, str(FFT_GENERATOR), "--out", str(FFT_HEADER)], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:

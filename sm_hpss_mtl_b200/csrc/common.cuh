@@ -110,6 +110,8 @@ void build_window(int n_fft, int win, float* out);
 // stage launchers (device pointers, enqueue on stream)
 int launch_stft(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* plan, int hop,
                 int power, float* S, float* cplx, cudaStream_t st);
+int launch_stft_fast(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* plan, int hop, int power,
+                     float* S, float* cplx, cudaStream_t st, bool* handled);
 int launch_median(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, int k, bool time_axis,
                   float* out, cudaStream_t st);
 int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm,

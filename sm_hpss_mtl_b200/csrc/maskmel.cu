@@ -14,6 +14,8 @@
 // a coalesced 128-byte row segment); the 8 warps split the frequency rows (mask phase) and
 // the mel filters (projection phase); masked values are staged through shared memory in
 // chunks of 64 frequency rows.
+#include <stdlib.h>
+
 #include "maskmath.cuh"
 
 namespace hpss {
@@ -328,8 +330,12 @@ int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const fl
     if (hpss_mode && mel && sweep) {
         const int64_t n_warps = (total + 31) / 32;
         const unsigned grid = (unsigned)((n_warps + kWarps - 1) / kWarps);
-        mask_mel_sweep_kernel<4><<<grid, kThreads, 0, st>>>(S, harm, perc, b->d_frame_off, b->d_block_clip, total, rows,
-                                                            sweep, n_mels, log_power, amin, out, clip_max);
+        static const int U = getenv("HPSS_SWEEP_U") ? atoi(getenv("HPSS_SWEEP_U")) : 4;   // development knob
+#define HPSS_SWEEP_LAUNCH(UU)                                                                                       \
+        mask_mel_sweep_kernel<UU><<<grid, kThreads, 0, st>>>(S, harm, perc, b->d_frame_off, b->d_block_clip, total,  \
+                                                             rows, sweep, n_mels, log_power, amin, out, clip_max)
+        if (U == 2) HPSS_SWEEP_LAUNCH(2); else if (U == 8) HPSS_SWEEP_LAUNCH(8); else if (U == 6) HPSS_SWEEP_LAUNCH(6); else HPSS_SWEEP_LAUNCH(4);
+#undef HPSS_SWEEP_LAUNCH
         HPSS_LAUNCHED("mask_mel_sweep_kernel");
         return HPSS_OK;
     }

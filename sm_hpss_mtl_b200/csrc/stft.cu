@@ -6,6 +6,8 @@
 // is read from HBM once per tile), every frame is transformed as a real-via-complex FFT
 // of size n_fft/2 entirely in shared memory, and the magnitudes are written transposed
 // so that consecutive lanes write consecutive frames of one frequency row.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -283,6 +285,14 @@ int choose_stft_tt(const hpss_ctx* ctx, const hpss_batch* b, int n_fft, int hop)
 
 int launch_stft(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* plan, int hop, int power,
                 float* S, float* cplx, cudaStream_t st) {
+    {   // specialised two-pass register FFT for the reference's (n_fft, hop) pairs
+        static const bool no_fast = getenv("HPSS_NO_FAST_STFT") != nullptr;   // development knob
+        bool handled = false;
+        if (!no_fast) {
+            const int rc = launch_stft_fast(ctx, b, wave, plan, hop, power, S, cplx, st, &handled);
+            if (rc || handled) return rc;
+        }
+    }
     const int tt = choose_stft_tt(ctx, b, plan->n_fft, hop);
     if (tt <= 0) {
         set_error("n_fft=%d does not fit the shared-memory FFT (max %d bytes)", plan->n_fft,

@@ -1,0 +1,215 @@
+// K1, specialised: fused framing + window + two-pass register FFT + |X| for the (n_fft, hop) pairs the
+// reference and BASELINE.json use (400/160, 512/160, 512/128, 1024/256, 2048/512).
+//
+// Replaces librosa.core.stft(center=False) + np.abs (lib/preprocessing.py:381,387,407,417,429,439).
+// Same tiling as the generic kernel in stft.cu (one CTA = up to 16 consecutive frames of one clip, each sample
+// read from HBM once), but every size is a compile-time constant:
+//   * real FFT of size n_fft = complex FFT of size N2 = n_fft/2 on (even, odd) sample pairs;
+//   * N2 = NA x NB.  Pass 1: for each b < NB a register DFT of size NA over the points NB*q + b (window multiply
+//     fused into the loads); pass 2: for each k1 < NA the twiddles W_N2^(b*k1) and a register DFT of size NB
+//     over b, written back in place -- which leaves the spectrum in natural order, so there are only two
+//     shared-memory round trips (the generic kernel makes one per radix) and no index arithmetic at run time;
+//   * the DFTs are generated straight-line codelets (tools/gen_fft_codelets.py), twiddles are literals;
+//   * lane = frame everywhere (half-warps of 16 frames): the frame stride of the spectrum buffer (N2 + 1
+//     float2) and of the padded sample staging ((hop + pad)/2 float2, pad chosen so that it is odd) make every
+//     shared-memory access conflict free, and the magnitudes leave as 64-byte runs of one frequency row.
+#include "common.cuh"
+#include "fft_codelets_gen.cuh"
+
+namespace hpss {
+
+namespace {
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <int NFFT, int HOP, int NA, int NB, int NT>
+struct FastCfg {
+    static constexpr int N2 = NFFT / 2;
+    static constexpr int TT = 16;
+    static constexpr int ZS = N2 | 1;                                   // float2 stride between frames
+    static constexpr int PAD = ((HOP / 2) % 2 == 0) ? 2 : 0;            // (HOP + PAD) / 2 odd
+    static constexpr int HOPP = HOP + PAD;
+    static constexpr int SEG = (TT - 1) * HOP + NFFT;                   // samples of a full tile
+    static constexpr int SEGP = SEG + PAD * ((SEG + HOP - 1) / HOP);    // padded
+    static constexpr int G = NT / 16;                                   // half-warp groups per CTA
+    static constexpr size_t smem_bytes =
+        sizeof(float2) * ((size_t)TT * ZS + N2 + (N2 / 2 + 1)) + sizeof(float) * ((size_t)NFFT + SEGP + 4);
+    static_assert(NA * NB == N2, "N2 = NA * NB");
+    static_assert(HOP % (2 * NB) == 0, "pad offsets must be compile-time constants");
+    static_assert(HOP % 4 == 0 && NT % 32 == 0, "vector staging");
+};
+
+template <int NFFT, int HOP, int NA, int NB, int NT>
+__global__ void __launch_bounds__(NT)
+stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sample_off,
+                 const int64_t* __restrict__ frame_off, const int2* __restrict__ tiles,
+                 const float* __restrict__ window, const float2* __restrict__ tw_half,
+                 const float2* __restrict__ tw_full, int power, float* __restrict__ S, float2* __restrict__ cplx) {
+    using C = FastCfg<NFFT, HOP, NA, NB, NT>;
+    constexpr int N2 = C::N2, ZS = C::ZS, PAD = C::PAD, HOPP = C::HOPP, G = C::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Z = reinterpret_cast<float2*>(smem_raw);            // [TT][ZS]
+    float2* s_twh = Z + (size_t)C::TT * ZS;                     // [N2]      exp(-2 pi i k / N2)
+    float2* s_twf = s_twh + N2;                                 // [N2/2+1]  exp(-2 pi i k / NFFT)
+    float* s_win = reinterpret_cast<float*>(s_twf + (N2 / 2 + 1));
+    float* s_samp = s_win + NFFT;                               // padded: sample s at s + PAD * (s / HOP)
+
+    const int tid = threadIdx.x;
+    const int2 tile = tiles[blockIdx.x];
+    const int c = tile.x, t0 = tile.y;
+    const int64_t fo = frame_off[c];
+    const int T = (int)(frame_off[c + 1] - fo);
+    const int nf = min(C::TT, T - t0);
+
+    // ---- stage tables and the sample segment
+    for (int i = tid; i < NFFT / 2; i += NT)
+        reinterpret_cast<float2*>(s_win)[i] = __ldg(reinterpret_cast<const float2*>(window) + i);
+    for (int i = tid; i < N2; i += NT) s_twh[i] = __ldg(tw_half + i);
+    for (int i = tid; i <= N2 / 2; i += NT) s_twf[i] = __ldg(tw_full + i);
+    {
+        const float* src = wave + sample_off[c] + (int64_t)t0 * HOP;
+        const int seg = (nf - 1) * HOP + NFFT;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const float4* src4 = reinterpret_cast<const float4*>(src);
+            for (int i = tid; i < seg / 4; i += NT) {
+                const float4 v = __ldg(src4 + i);
+                const int s = 4 * i;
+                float2* d = reinterpret_cast<float2*>(s_samp + s + PAD * (s / HOP));
+                d[0] = make_float2(v.x, v.y);
+                d[1] = make_float2(v.z, v.w);
+            }
+        } else {
+            for (int s = tid; s < seg; s += NT) s_samp[s + PAD * (s / HOP)] = __ldg(src + s);
+        }
+    }
+    __syncthreads();
+
+    const int fr = tid & 15;
+    const int g = tid >> 4;
+    const bool live = fr < nf;
+
+    // ---- pass 1: DFT-NA over q of w[n] x[n], n = NB*q + b  ->  Y[b][k1] at NA*b + k1
+    if (live) {
+        const float2* xs = reinterpret_cast<const float2*>(s_samp + fr * HOPP);
+        const float2* ws = reinterpret_cast<const float2*>(s_win);
+#pragma unroll 1
+        for (int b = g; b < NB; b += G) {
+            float2 v[NA];
+#pragma unroll
+            for (int q = 0; q < NA; ++q) {
+                const int j0 = NB * q;                                   // compile-time after unrolling
+                const int po = (2 * j0 + PAD * ((2 * j0) / HOP)) / 2;    // float2 offset in the padded staging
+                const float2 xv = xs[po + b];
+                const float2 wv = ws[j0 + b];
+                v[q] = make_float2(xv.x * wv.x, xv.y * wv.y);
+            }
+            Dft<NA>::run(v);
+            float2* z = Z + fr * ZS + NA * b;
+#pragma unroll
+            for (int k1 = 0; k1 < NA; ++k1) z[k1] = v[k1];
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 2: twiddle W_N2^(b*k1), DFT-NB over b  ->  Z[k1 + NA*k2], in place (natural order)
+    if (live) {
+#pragma unroll 1
+        for (int k1 = g; k1 < NA; k1 += G) {
+            float2 v[NB];
+            float2* z = Z + fr * ZS + k1;
+            v[0] = z[0];
+#pragma unroll
+            for (int b = 1; b < NB; ++b) {
+                const float2 a = z[NA * b];
+                const float2 w = s_twh[b * k1];
+                v[b] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+            }
+            Dft<NB>::run(v);
+#pragma unroll
+            for (int k2 = 0; k2 < NB; ++k2) z[NA * k2] = v[k2];
+        }
+    }
+    __syncthreads();
+
+    // ---- real-FFT unpack + magnitude, written (f, t) with lanes along t.  Bins k and N2-k share their loads:
+    // X[k] = E + W*O and X[N2-k] = conj(E - W*O) with E, O from Z[k] and conj(Z[N2-k]).
+    if (live) {
+        const int F = N2 + 1;
+        const float2* zrow = Z + fr * ZS;
+        const int64_t base = (int64_t)F * fo + t0 + fr;
+        float* Sg = S + base;
+        float2* Cg = cplx ? cplx + base : nullptr;
+#pragma unroll 2
+        for (int k = g; k <= N2 / 2; k += G) {
+            const int k2 = N2 - k;
+            const float2 zk = zrow[k];
+            float2 zc = zrow[k == 0 ? 0 : k2];
+            zc.y = -zc.y;
+            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+            const float2 dd = make_float2(zk.x - zc.x, zk.y - zc.y);
+            const float2 o = make_float2(0.5f * dd.y, -0.5f * dd.x);
+            const float2 w = s_twf[k];
+            const float2 wo = make_float2(w.x * o.x - w.y * o.y, w.x * o.y + w.y * o.x);
+            const float2 xa = make_float2(e.x + wo.x, e.y + wo.y);      // X[k]
+            const float2 xb = make_float2(e.x - wo.x, wo.y - e.y);      // X[N2-k] = conj(E - W*O)
+            const float pa = xa.x * xa.x + xa.y * xa.y;
+            const float pb = xb.x * xb.x + xb.y * xb.y;
+            const int64_t ga = (int64_t)k * T, gb = (int64_t)k2 * T;
+            Sg[ga] = power ? pa : fast_sqrt(pa);
+            if (Cg) Cg[ga] = xa;
+            if (k2 != k) {
+                Sg[gb] = power ? pb : fast_sqrt(pb);
+                if (Cg) Cg[gb] = xb;
+            }
+        }
+    }
+}
+
+template <int NFFT, int HOP, int NA, int NB, int NT>
+int launch_cfg(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* plan, int power, float* S, float* cplx,
+               cudaStream_t st) {
+    using C = FastCfg<NFFT, HOP, NA, NB, NT>;
+    if (C::smem_bytes > (size_t)ctx->max_smem_optin) {
+        set_error("n_fft=%d does not fit the shared-memory FFT (max %d bytes)", NFFT, ctx->max_smem_optin);
+        return HPSS_ERR_UNSUPPORTED;
+    }
+    // tile height: at most 16 frames, an even split of the longest clip
+    int tt = C::TT;
+    if (b->max_frames > 0) {
+        const int64_t nt = (b->max_frames + tt - 1) / tt;
+        tt = (int)((b->max_frames + nt - 1) / nt);
+    }
+    int rc = ensure_stft_tiles(b, tt);
+    if (rc) return rc;
+    if (b->n_stft_tiles == 0) return HPSS_OK;
+    auto kern = stft_fast_kernel<NFFT, HOP, NA, NB, NT>;
+    HPSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
+    kern<<<b->n_stft_tiles, NT, C::smem_bytes, st>>>(wave, b->d_sample_off, b->d_frame_off, b->d_stft_tiles,
+                                                     plan->d_window, plan->d_tw_half, plan->d_tw_full, power, S,
+                                                     reinterpret_cast<float2*>(cplx));
+    HPSS_LAUNCHED("stft_fast_kernel");
+    return HPSS_OK;
+}
+
+}  // namespace
+
+// *handled = false (nothing launched) when (n_fft, hop) has no specialisation; the caller then runs the
+// generic mixed-radix kernel.
+int launch_stft_fast(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* plan, int hop, int power, float* S,
+                     float* cplx, cudaStream_t st, bool* handled) {
+    *handled = true;
+    const int n = plan->n_fft;
+    if (n == 400 && hop == 160) return launch_cfg<400, 160, 10, 20, 160>(ctx, b, wave, plan, power, S, cplx, st);
+    if (n == 512 && hop == 160) return launch_cfg<512, 160, 16, 16, 256>(ctx, b, wave, plan, power, S, cplx, st);
+    if (n == 512 && hop == 128) return launch_cfg<512, 128, 16, 16, 256>(ctx, b, wave, plan, power, S, cplx, st);
+    if (n == 1024 && hop == 256) return launch_cfg<1024, 256, 16, 32, 256>(ctx, b, wave, plan, power, S, cplx, st);
+    if (n == 2048 && hop == 512) return launch_cfg<2048, 512, 32, 32, 256>(ctx, b, wave, plan, power, S, cplx, st);
+    *handled = false;
+    return HPSS_OK;
+}
+
+}  // namespace hpss
