@@ -129,7 +129,10 @@ __device__ __forceinline__ void tile_store(const float* __restrict__ sm, float* 
 // compute warps run the selection networks on earlier tiles; full/empty mbarriers per buffer.
 // Item n of a CTA uses buffer n % NB and is consumed by compute warp n % kComputeWarps.
 constexpr int kComputeWarps = 8;
-constexpr int kLoaderWarps = 2;
+#ifndef HPSS_LOADER_WARPS
+#define HPSS_LOADER_WARPS 4
+#endif
+constexpr int kLoaderWarps = HPSS_LOADER_WARPS;
 constexpr int kRingThreads = (kComputeWarps + kLoaderWarps) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -249,11 +252,11 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
         for (int64_t n = 0; n < my_items; ++n) {
             const int b = (int)(n % NB);
             const uint32_t use = (uint32_t)(n / NB);
-            if (use > 0) mbar_wait(empty0 + 8u * b, (use - 1) & 1u);
             const int64_t item = blockIdx.x + n * gridDim.x;
             const int64_t lb = item / n_ptiles;
             const int p0 = (int)(item - lb * n_ptiles) * TT;
             const LineInfo li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane);
+            if (use > 0) mbar_wait(empty0 + 8u * b, (use - 1) & 1u);
             tile_fill_async<TIME_AXIS>(smem_u32(smem + (size_t)b * tile_floats), S, li, lane, lw, p0, HALO, span, lstride);
             cp_async_arrive(full0 + 8u * b);
         }
@@ -276,13 +279,26 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
 #pragma unroll
                     for (int i = 0; i < K + G - 1; ++i) x[i] = sm[sidx<TIME_AXIS>(lane, g * G + i, lstride)];
                     MedianGroup<K>::run(x, o);
+                    if (TIME_AXIS) {
+                        // in place: a lane's outputs are consecutive in time, the coalesced store needs the
+                        // transposed view of the tile (tile_store below)
 #pragma unroll
-                    for (int j = 0; j < G; ++j) sm[sidx<TIME_AXIS>(lane, g * G + j, lstride)] = o[j];
+                        for (int j = 0; j < G; ++j) sm[sidx<TIME_AXIS>(lane, g * G + j, lstride)] = o[j];
+                    } else {
+                        // lane = frame: registers -> global memory is already one 128-byte row segment per output
+                        float* dst = out + li.base + (int64_t)(p0 + g * G) * li.estride;
+                        const int nj = min(G, li.n - p0 - g * G);
+#pragma unroll
+                        for (int j = 0; j < G; ++j)
+                            if (j < nj) dst[(int64_t)j * li.estride] = o[j];
+                    }
                 }
             }
             __syncwarp();
-            tile_store<TIME_AXIS>(sm, out, li, lane, p0, TT, lstride);
-            __syncwarp();
+            if (TIME_AXIS) {
+                tile_store<TIME_AXIS>(sm, out, li, lane, p0, TT, lstride);
+                __syncwarp();
+            }
             if (lane == 0) mbar_arrive(empty0 + 8u * b);
         }
     }

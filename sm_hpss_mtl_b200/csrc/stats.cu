@@ -19,76 +19,123 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Raw moments.  grid = (frame chunks, groups of 8 feature rows): every warp owns ONE feature row
-// for its whole life and walks the clips of its frame chunk (lanes along time, coalesced 128-byte
-// reads); per-lane float64 accumulators (one sum per class + the sum of squares) stay in
-// registers and are reduced across the warp once, at the end: 1 + n_classes float64 atomics per warp.
+// Raw moments.  grid = (frame chunks, groups of 8 row pairs): every warp owns TWO feature rows (d and
+// d + ceil(D/2): for the HPSS features the same band of the harmonic and the percussive stream) for its whole
+// life and walks the clips of its frame chunk in blocks of 128 frames (lanes along time, four coalesced
+// 128-byte reads per row and block, eight loads in flight per warp; the per-clip set-up -- offsets, class,
+// thresholds -- is shared by the two rows).  Within a block every lane adds at most four values in float32;
+// the block's partial sum and sum of squares are then folded into per-lane float64 accumulators (one sum per
+// class + the sum of squares, per row) that stay in registers and are reduced across the warp once, at the
+// end: 1 + n_classes float64 atomics per row and warp.
+// A non-finite value makes the block's float32 sum of squares non-finite; the block is then redone value by
+// value (non-finite values are counted and contribute 0).
 // CLIP: fused K3b -- x = max(x, max_clip_stream - top_db) is applied (and written back) on the way.
+template <bool CLIP>
+__device__ __forceinline__ void block_load(float* row, int n, int lane, float (&x)[4]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int t = lane + 32 * u;
+        x[u] = 0.f;
+        if (t < n) x[u] = CLIP ? row[t] : __ldg(row + t);
+    }
+}
+
 template <int MAXC, bool CLIP>
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ void block_fold(float* row, int n, int cls, float thr, int lane, float (&x)[4],
+                                           double (&s)[MAXC], double& q, unsigned& bad) {
+    float ps = 0.f, pq = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int t = lane + 32 * u;
+        if (CLIP) {
+            if (t < n && x[u] < thr) { x[u] = thr; row[t] = thr; }
+        }
+        ps += x[u];
+        pq = fmaf(x[u], x[u], pq);
+    }
+    if (!isfinite(pq)) {          // rare: redo this lane's values one by one
+        ps = 0.f; pq = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v = x[u];
+            if (!isfinite(v)) { v = 0.f; ++bad; }
+            if (fabsf(v) > 1e18f) {   // the square would overflow float32: fold this value in float64
+                q = fma((double)v, (double)v, q);
+#pragma unroll
+                for (int k = 0; k < MAXC; ++k) if (k == cls) s[k] += (double)v;
+                v = 0.f;
+            }
+            ps += v;
+            pq = fmaf(v, v, pq);
+        }
+    }
+    const double psd = (double)ps;
+    q += (double)pq;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) if (k == cls) s[k] += psd;
+}
+
+template <int MAXC, bool CLIP>
+__global__ void __launch_bounds__(kThreads, 3)
 moments_kernel(float* __restrict__ feat, const int64_t* __restrict__ frame_off,
                const int32_t* __restrict__ block_clip, int n_clips, int64_t total_frames, int64_t chunk_frames,
                int D, const int32_t* __restrict__ clip_class, int n_classes, double* __restrict__ g_sum,
                double* __restrict__ g_sumsq, double* __restrict__ g_count, double* __restrict__ g_nonfinite,
                const uint32_t* __restrict__ clip_max, int rows_per_stream, int n_streams, float top_db) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int d = blockIdx.y * kWarps + warp;
-    if (d < D) {
-        double s[MAXC];
+    const int half = (D + 1) / 2;
+    const int d0 = blockIdx.y * kWarps + warp;        // first row of this warp; the second is d0 + half
+    if (d0 < half) {
+        const int d1 = d0 + half;
+        const bool two = d1 < D;
+        double s0[MAXC], s1[MAXC];
 #pragma unroll
-        for (int k = 0; k < MAXC; ++k) s[k] = 0.0;
-        double q = 0.0;
+        for (int k = 0; k < MAXC; ++k) { s0[k] = 0.0; s1[k] = 0.0; }
+        double q0 = 0.0, q1 = 0.0;
         unsigned bad = 0;
+        const int st0 = CLIP ? d0 / rows_per_stream : 0;
+        const int st1 = CLIP ? (two ? d1 / rows_per_stream : st0) : 0;
         int64_t g0 = (int64_t)blockIdx.x * chunk_frames;
         const int64_t g1 = min(total_frames, g0 + chunk_frames);
         int c = find_clip_hint(frame_off, block_clip, g0);
+        int64_t fo = __ldg(frame_off + c), fe = __ldg(frame_off + c + 1);
         while (g0 < g1) {
-            const int64_t fo = __ldg(frame_off + c), fe = __ldg(frame_off + c + 1);
-            const int64_t seg_end = min(g1, fe);
-            const int T = (int)(fe - fo), len = (int)(seg_end - g0);
+            while (fe <= g0) { ++c; fo = fe; fe = __ldg(frame_off + c + 1); }   // next non-empty clip
+            const int T = (int)(fe - fo);
+            const int len = (int)(min(g1, fe) - g0);
             const int cls = __ldg(clip_class + c);
-            float* row = feat + (int64_t)D * fo + (int64_t)d * T + (g0 - fo);
-            float thr = -INFINITY;
-            if (CLIP) thr = ordered_to_float(__ldg(clip_max + (size_t)n_streams * c + d / rows_per_stream)) - top_db;
-            double ps = 0.0;
-            // four independent 128-byte loads in flight per warp (the trip count is a run-time value)
-            for (int t0 = lane; t0 < len; t0 += 128) {
-                float xv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int t = t0 + 32 * u;
-                    xv[u] = (t < len) ? (CLIP ? row[t] : __ldg(row + t)) : 0.f;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int t = t0 + 32 * u;
-                    if (t < len) {
-                        float x = xv[u];
-                        if (CLIP && x < thr) { x = thr; row[t] = x; }
-                        if (!isfinite(x)) { x = 0.f; ++bad; }
-                        const double xd = (double)x;
-                        ps += xd;
-                        q = fma(xd, xd, q);
-                    }
-                }
+            float thr0 = -INFINITY, thr1 = -INFINITY;
+            if (CLIP) {
+                const uint32_t* cm = clip_max + (size_t)n_streams * c;
+                thr0 = ordered_to_float(__ldg(cm + st0)) - top_db;
+                thr1 = ordered_to_float(__ldg(cm + st1)) - top_db;
             }
-#pragma unroll
-            for (int k = 0; k < MAXC; ++k) s[k] += (k == cls) ? ps : 0.0;
-            g0 = seg_end;
-            ++c;
-            while (g0 < g1 && __ldg(frame_off + c + 1) <= g0) ++c;   // skip empty clips
+            float* r0 = feat + (int64_t)D * fo + (int64_t)d0 * T + (g0 - fo);
+            float* r1 = r0 + (int64_t)half * T;
+            for (int t0 = 0; t0 < len; t0 += 128) {
+                const int n = min(128, len - t0);
+                float x0[4], x1[4];
+                block_load<CLIP>(r0 + t0, n, lane, x0);
+                block_load<CLIP>(r1 + t0, two ? n : 0, lane, x1);
+                block_fold<MAXC, CLIP>(r0 + t0, n, cls, thr0, lane, x0, s0, q0, bad);
+                block_fold<MAXC, CLIP>(r1 + t0, two ? n : 0, cls, thr1, lane, x1, s1, q1, bad);
+            }
+            g0 += len;
         }
-        q = warp_sum(q);
+        q0 = warp_sum(q0);
+        q1 = warp_sum(q1);
 #pragma unroll
         for (int k = 0; k < MAXC; ++k) {
             if (k < n_classes) {
-                const double t = warp_sum(s[k]);
-                if (lane == 0 && t != 0.0) atomicAdd(g_sum + (size_t)k * D + d, t);
+                const double t0 = warp_sum(s0[k]), t1 = warp_sum(s1[k]);
+                if (lane == 0 && t0 != 0.0) atomicAdd(g_sum + (size_t)k * D + d0, t0);
+                if (lane == 0 && two && t1 != 0.0) atomicAdd(g_sum + (size_t)k * D + d1, t1);
             }
         }
         bad = __reduce_add_sync(0xffffffffu, bad);
         if (lane == 0) {
-            if (q != 0.0) atomicAdd(g_sumsq + d, q);
+            if (q0 != 0.0) atomicAdd(g_sumsq + d0, q0);
+            if (two && q1 != 0.0) atomicAdd(g_sumsq + d1, q1);
             if (bad) atomicAdd(g_nonfinite, (double)bad);
         }
     }
@@ -183,7 +230,7 @@ static int launch_moments_impl(hpss_ctx* ctx, const hpss_batch* b, float* feat, 
         return HPSS_ERR_UNSUPPORTED;
     }
     // frame chunks: multiples of 32 frames, enough CTAs for ~8 waves of 8 resident CTAs per SM
-    const int row_groups = (D + kWarps - 1) / kWarps;
+    const int row_groups = ((D + 1) / 2 + kWarps - 1) / kWarps;   // a warp owns two rows
     int64_t want_chunks = ((int64_t)ctx->sm_count * 64 + row_groups - 1) / row_groups;
     int64_t chunk = (total + want_chunks - 1) / want_chunks;
     chunk = (chunk + 31) / 32 * 32;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""One bench step (BASELINE.json configs[1]) for ncu: 2 warm-up steps (12 launches) + 1 step.
+"""Three bench steps (BASELINE.json configs[1], hpss_featuregram_moments = 5 kernel launches each) for ncu.
 
-    ncu --set full --clock-control none --import-source on -s 12 -c 6 -o gpurun_out/prof python tools/profile_step.py
+    ncu --set full --clock-control none --import-source on -s 10 -c 5 -o gpurun_out/prof python tools/profile_step.py
 """
 import os
 import sys
@@ -27,7 +27,7 @@ out = torch.empty(D * batch.total_frames, device="cuda")
 cls = (np.arange(n_clips) % 3).astype(np.int32)
 acc = torch.zeros(3 * D + D + 4, dtype=torch.float64, device="cuda")
 for _ in range(3):
-    engine.featuregram(batch, wave, prm, out=out)
-    engine.moments(batch, out, D, cls, 3, acc=acc)
+    acc.zero_()
+    engine.featuregram_moments(batch, wave, prm, cls, 3, out=out, acc=acc)
 torch.cuda.synchronize()
 print("launches", engine.launch_count())
