@@ -274,7 +274,45 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
             mbar_wait(full0 + 8u * b, use & 1u);
             if (live) {
                 const int ng = min(NG, (li.n - p0 + G - 1) / G);
-                for (int g = 0; g < ng; ++g) {
+                int g = 0;
+                if constexpr (MedianStep<K>::available) {
+                    // stateful walk: two groups per step, the sorted blocks C2, C3 of one step are C0, C1 of the next
+                    static_assert(MedianStep<K>::G == G, "step and group networks must agree on G");
+                    constexpr int NR = MedianStep<K>::NRAW;
+                    if (ng >= 2) {
+                        float ca[G], cb[G];
+                        {
+                            float r0[G], r1[G];
+#pragma unroll
+                            for (int i = 0; i < G; ++i) {
+                                r0[i] = sm[sidx<TIME_AXIS>(lane, G - 1 + i, lstride)];
+                                r1[i] = sm[sidx<TIME_AXIS>(lane, 2 * G - 1 + i, lstride)];
+                            }
+                            MedianStep<K>::sort(r0, ca);
+                            MedianStep<K>::sort(r1, cb);
+                        }
+                        for (; g + 2 <= ng; g += 2) {
+                            float xr[NR], o[2 * G], na[G], nb[G];
+#pragma unroll
+                            for (int i = 0; i < NR; ++i)
+                                xr[i] = sm[sidx<TIME_AXIS>(lane, g * G + MedianStep<K>::raw_pos(i), lstride)];
+                            MedianStep<K>::run(ca, cb, xr, o, na, nb);
+#pragma unroll
+                            for (int i = 0; i < G; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
+                            if (TIME_AXIS) {
+#pragma unroll
+                                for (int j = 0; j < 2 * G; ++j) sm[sidx<TIME_AXIS>(lane, g * G + j, lstride)] = o[j];
+                            } else {
+                                float* dst = out + li.base + (int64_t)(p0 + g * G) * li.estride;
+                                const int nj = min(2 * G, li.n - p0 - g * G);
+#pragma unroll
+                                for (int j = 0; j < 2 * G; ++j)
+                                    if (j < nj) dst[(int64_t)j * li.estride] = o[j];
+                            }
+                        }
+                    }
+                }
+                for (; g < ng; ++g) {
                     float x[K + G - 1], o[G];
 #pragma unroll
                     for (int i = 0; i < K + G - 1; ++i) x[i] = sm[sidx<TIME_AXIS>(lane, g * G + i, lstride)];

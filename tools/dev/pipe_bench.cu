@@ -8,6 +8,7 @@
 
 template <int MODE>
 __global__ void k(float* out, int* iout, long long* cyc, float seed) {
+    const int one = (int)gridDim.y, mone = -(int)gridDim.z;
     float a[UNROLL], b = seed + threadIdx.x, c = seed * 0.5f;
     int ia[UNROLL], ib = (int)seed + threadIdx.x, ic = 3;
     float2 p[UNROLL / 2];
@@ -42,6 +43,15 @@ __global__ void k(float* out, int* iout, long long* cyc, float seed) {
             if (MODE == 10) a[i] = fminf(fminf(a[i], a[(i + 5) % UNROLL]), a[(i + 9) % UNROLL]);     // FMNMX3
             if (MODE == 11) { if (i % 3 == 0) ia[i] = ia[i] * ib + ic; else MN(i, 6); }               // 2 FMNMX : 1 IMAD
             if (MODE == 12) { if (i % 4 == 0) ia[i] = ia[i] * ib + ic; else MN(i, 8); }               // 3 FMNMX : 1 IMAD
+            if (MODE == 13) ia[i] = ia[i] + ia[(i + 5) % UNROLL] - ia[(i + 9) % UNROLL];               // IADD3
+            if (MODE == 14 && (i & 1) == 0) {   // compare-exchange, both FMNMX (2 instr per pair i, i+1)
+                const float lo = fminf(a[i], a[i + 1]), hi = fmaxf(a[i], a[i + 1]); a[i] = lo; a[i + 1] = hi;
+            }
+            if (MODE == 15 && (i & 1) == 0) {   // compare-exchange: FMNMX + 2 IMAD with run-time +1 / -1 (3 instr per pair)
+                const float lo = fminf(a[i], a[i + 1]);
+                const int s2 = __float_as_int(a[i]) * one + __float_as_int(a[i + 1]);
+                a[i + 1] = __int_as_float(__float_as_int(lo) * mone + s2); a[i] = lo;
+            }
         }
 #pragma unroll
         for (int i = 0; i < UNROLL; ++i) {      // pass B (max instead of min so that nothing can be merged)
@@ -66,6 +76,15 @@ __global__ void k(float* out, int* iout, long long* cyc, float seed) {
             if (MODE == 10) a[i] = fmaxf(fmaxf(a[i], a[(i + 3) % UNROLL]), a[(i + 7) % UNROLL]);
             if (MODE == 11) { if (i % 3 == 0) ia[i] = ia[i] * ic + ib; else MX(i, 3); }
             if (MODE == 12) { if (i % 4 == 0) ia[i] = ia[i] * ic + ib; else MX(i, 4); }
+            if (MODE == 13) ia[i] = ia[i] + ia[(i + 3) % UNROLL] - ia[(i + 7) % UNROLL];
+            if (MODE == 14 && (i & 1) == 1 && i + 1 < UNROLL) {
+                const float lo = fminf(a[i], a[i + 1]), hi = fmaxf(a[i], a[i + 1]); a[i] = lo; a[i + 1] = hi;
+            }
+            if (MODE == 15 && (i & 1) == 1 && i + 1 < UNROLL) {
+                const float lo = fminf(a[i], a[i + 1]);
+                const int s2 = __float_as_int(a[i]) * one + __float_as_int(a[i + 1]);
+                a[i + 1] = __int_as_float(__float_as_int(lo) * mone + s2); a[i] = lo;
+            }
         }
     }
     long long t1 = clock64();
@@ -106,6 +125,9 @@ int main() {
         run<7>("FMNMX+IMAD 1:1", w, UNROLL);
         run<11>("FMNMX+IMAD 2:1", w, UNROLL);
         run<12>("FMNMX+IMAD 3:1", w, UNROLL);
+        run<13>("IADD3", w, UNROLL);
+        run<14>("CE = 2 FMNMX   (per CE)", w, (2 * UNROLL - 1) / 4);
+        run<15>("CE = FMNMX + 2 IMAD (per CE)", w, (2 * UNROLL - 1) / 4);
         run<8>("FFMA2 (f32x2)", w, UNROLL / 2);
         run<9>("FADD2 (f32x2)", w, UNROLL / 2);
     }

@@ -54,22 +54,49 @@ class Prog:
     def mx(self, a, b):
         return self.op('max', a, b)
 
+    def cemax(self, a, b, lo):
+        """max(a, b) given lo = min(a, b): a + b - lo on the 32-bit patterns (exact, wraps mod 2^32).
+        Integer adds can issue on the FMA pipe (IMAD.IADD) while FMNMX occupies the half-rate ALU pipe."""
+        d = self.nreg
+        self.nreg += 1
+        self.ops.append((d, 'cemax', a, b, lo))
+        return d
+
     def dce(self):
+        # a cemax whose min has no other user becomes a plain max (and the min dies)
+        users = {}
+        for op in self.ops:
+            for src in op[2:]:
+                users[src] = users.get(src, 0) + 1
+        for o in self.outs:
+            users[o] = users.get(o, 0) + 1
+        ops = []
+        for op in self.ops:
+            if op[1] == 'cemax' and users.get(op[4], 0) == 1:
+                ops.append((op[0], 'max', op[2], op[3]))
+            else:
+                ops.append(op)
         live = set(self.outs)
         keep = []
-        for (d, kind, a, b) in reversed(self.ops):
-            if d in live:
-                keep.append((d, kind, a, b))
-                live.add(a)
-                live.add(b)
+        for op in reversed(ops):
+            if op[0] in live:
+                keep.append(op)
+                live.update(op[2:])
         self.ops = keep[::-1]
         return self
 
     def run(self, x):
         """x: (n_in, N) array -> (len(outs), N)."""
         regs = {i: x[i] for i in range(self.n_in)}
-        for (d, kind, a, b) in self.ops:
-            regs[d] = np.minimum(regs[a], regs[b]) if kind == 'min' else np.maximum(regs[a], regs[b])
+        for op in self.ops:
+            d, kind, a, b = op[:4]
+            if kind == 'min':
+                regs[d] = np.minimum(regs[a], regs[b])
+            elif kind == 'max':
+                regs[d] = np.maximum(regs[a], regs[b])
+            else:   # cemax: integer identity on the bit patterns
+                ia, ib, il = (regs[r].view(np.uint32) for r in (a, b, op[4]))
+                regs[d] = (ia + ib - il).view(np.float32)
         return np.stack([regs[o] for o in self.outs])
 
 
@@ -104,12 +131,20 @@ def batcher_pairs(n):
     return [(i, j) for (i, j) in pairs if j < n]
 
 
+INT_EVERY = 0      # every INT_EVERY-th compare-exchange gets its max from integer adds (0 = never)
+_ce_count = [0]
+
+
 def sort_wires(P: Prog, wires):
     """Apply a sorting network to the SSA values in ``wires``; returns sorted wires."""
     w = list(wires)
     for (i, j) in batcher_pairs(len(w)):
         lo = P.mn(w[i], w[j])
-        hi = P.mx(w[i], w[j])
+        _ce_count[0] += 1
+        if INT_EVERY and _ce_count[0] % INT_EVERY == 0:
+            hi = P.cemax(w[i], w[j], lo)
+        else:
+            hi = P.mx(w[i], w[j])
         w[i], w[j] = lo, hi
     return w
 
@@ -133,6 +168,126 @@ def merge_select(P: Prog, A, B, r):
     for t in terms[1:]:
         v = P.mn(v, t)
     return v
+
+
+def oe_merge_pairs(n):
+    """Comparators of Batcher's odd-even merge of two sorted halves (n a power of two, wires 0..n-1)."""
+    pairs = []
+
+    def merge(lo, hi, r):
+        step = r * 2
+        if step < hi - lo:
+            merge(lo, hi, step)
+            merge(lo + r, hi, step)
+            for i in range(lo + r, hi - r, step):
+                pairs.append((i, i + r))
+        else:
+            pairs.append((lo, lo + r))
+
+    merge(0, n - 1, 1)
+    return pairs
+
+
+def merge_lists(P: Prog, A, B, cache):
+    """Full merge of two sorted wire lists of any lengths (virtual +inf padding); memoised."""
+    key = (tuple(A), tuple(B))
+    if key in cache:
+        return cache[key]
+    if not A or not B:
+        return list(A) + list(B)
+    n = 1
+    while n < max(len(A), len(B)):
+        n *= 2
+    INF = None
+    w = list(A) + [INF] * (n - len(A)) + list(B) + [INF] * (n - len(B))
+    for (i, j) in oe_merge_pairs(2 * n):
+        a, b = w[i], w[j]
+        if b is INF:
+            continue
+        if a is INF:
+            w[i], w[j] = b, INF
+            continue
+        w[i], w[j] = P.mn(a, b), P.mx(a, b)
+    out = [v for v in w if v is not INF]
+    cache[key] = out
+    return out
+
+
+def shared_extras(P: Prog, X, G, cache):
+    """sorted X[j+1 .. j+G-2] for j = 0, 2, .., G-2, built from nested suffix sorts of the left extras
+    X[:G-1] and nested prefix sorts of the right extras X[G-1:] (each pair of values is sorted once)."""
+    L, R = X[:G - 1], X[G - 1:]
+    suf, pre = {0: []}, {0: []}
+    for k in range(2, G - 1, 2):
+        suf[k] = merge_lists(P, sort_wires(P, [L[G - 1 - k], L[G - k]]), suf[k - 2], cache)
+        pre[k] = merge_lists(P, pre[k - 2], sort_wires(P, [R[k - 2], R[k - 1]]), cache)
+    return {j: merge_lists(P, suf[G - 2 - j], pre[j], cache) for j in range(0, G, 2)}
+
+
+def step_raw_index(K, G):
+    """window-relative input positions a stateful step reads raw (see gen_step)"""
+    return list(range(0, G - 1)) + list(range(G, 2 * G - 1)) + list(range(3 * G - 1, K + 2 * G - 1))
+
+
+def gen_step(K, G):
+    """Stateful double step for K = 4G - 1: 2G consecutive outputs per call, walking along a line.
+
+    With x[i] the inputs of the 2G windows (x[j .. j+K-1] for output j), the blocks
+    C0 = x[G-1..2G-2], C1 = x[2G-1..3G-2], C2 = x[3G-1..4G-2], C3 = x[4G-1..5G-2] tile the two cores
+    (outputs 0..G-1: C0 u C1 u C2, outputs G..2G-1: C1 u C2 u C3).  C0 and C1 arrive SORTED from the previous
+    step (its C2, C3); C2, C3 are sorted here and handed on; C1 u C2 is merged once and serves both cores.
+    Program inputs: ca[G], cb[G] (sorted), then the raw values x[i], i in step_raw_index(K, G).
+    Program outputs: o[2G], then sorted C2[G], C3[G]."""
+    assert K == 4 * G - 1 and G % 2 == 0
+    h = K // 2
+    raw_idx = step_raw_index(K, G)
+    P = Prog(2 * G + len(raw_idx))
+    ca, cb = list(range(0, G)), list(range(G, 2 * G))
+    xw = {i: 2 * G + n for n, i in enumerate(raw_idx)}
+    cache = {}
+    cc = sort_wires(P, [xw[i] for i in range(3 * G - 1, 4 * G - 1)])
+    cd = sort_wires(P, [xw[i] for i in range(4 * G - 1, 5 * G - 1)])
+    pair = merge_lists(P, cb, cc, cache)
+    outs = []
+    for (core, base) in ((merge_lists(P, ca, pair, cache), 0), (merge_lists(P, pair, cd, cache), G)):
+        m = core[h - G + 1:h + 1]
+        X = [xw[base + i] for i in range(0, G - 1)] + [xw[base + K + i] for i in range(0, G - 1)]
+        sh = shared_extras(P, X, G, cache)
+        o = [None] * G
+        for j in range(0, G, 2):
+            u = merge_select(P, m, sh[j], G - 2)
+            w = merge_select(P, m, sh[j], G - 1)
+            o[j] = P.mx(u, P.mn(X[j], w))
+            o[j + 1] = P.mx(u, P.mn(X[j + G - 1], w))
+        outs += o
+    P.outs = outs + cc + cd
+    return P.dce()
+
+
+def verify_step(P: Prog, K, G, trials=600, steps=4, seed=0):
+    rng = np.random.default_rng(seed + 977 * K)
+    raw_idx = step_raw_index(K, G)
+    L = K - 1 + 2 * G * steps
+    for data in (rng.standard_normal((L, trials)).astype(np.float32),
+                 rng.integers(0, 3, size=(L, trials)).astype(np.float32),
+                 np.sort(rng.standard_normal((L, trials)).astype(np.float32), axis=0)):
+        ca = np.sort(data[G - 1:2 * G - 1], axis=0)
+        cb = np.sort(data[2 * G - 1:3 * G - 1], axis=0)
+        for st in range(steps):
+            base = 2 * G * st
+            x = data[base:base + K + 2 * G - 1]
+            res = P.run(np.concatenate([ca, cb, x[raw_idx]], axis=0))
+            for j in range(2 * G):
+                if not np.array_equal(res[j], np.sort(data[base + j:base + j + K], axis=0)[K // 2]):
+                    return False
+            ca, cb = res[2 * G:3 * G], res[3 * G:4 * G]
+    return True
+
+
+def gen_sort(n):
+    P = Prog(n)
+    P.outs = sort_wires(P, list(range(n)))
+    return P.dce()
 
 
 def gen_group(K, G, pair=True):
@@ -199,11 +354,63 @@ def emit_cuda(P: Prog, K, G, name):
     def ref(r):
         return f"x[{r}]" if r < P.n_in else f"t{r}"
 
-    for (d, kind, a, b) in P.ops:
-        f = 'fminf' if kind == 'min' else 'fmaxf'
-        lines.append(f"  const float t{d} = {f}({ref(a)}, {ref(b)});")
+    lines += emit_ops(P, ref)
     for j, o in enumerate(P.outs):
         lines.append(f"  o[{j}] = {ref(o)};")
+    lines.append("}")
+    return "\n".join(lines)
+
+
+def emit_ops(P: Prog, ref):
+    lines = []
+    for op in P.ops:
+        d, kind, a, b = op[:4]
+        if kind == 'cemax':
+            lines.append(f"  const float t{d} = __int_as_float(__float_as_int({ref(a)}) + __float_as_int({ref(b)}) - "
+                         f"__float_as_int({ref(op[4])}));")
+        else:
+            f = 'fminf' if kind == 'min' else 'fmaxf'
+            lines.append(f"  const float t{d} = {f}({ref(a)}, {ref(b)});")
+    return lines
+
+
+def emit_step_cuda(P: Prog, K, G):
+    """median_step_kK(ca, cb, xr, o, na, nb): see gen_step."""
+    nr = len(step_raw_index(K, G))
+    lines = [f"// K={K} stateful double step: {len(P.ops)} min/max ops = {len(P.ops) / (2 * G):.1f} per output",
+             f"__device__ __forceinline__ void median_step_k{K}(const float (&ca)[{G}], const float (&cb)[{G}], "
+             f"const float (&xr)[{nr}], float (&o)[{2 * G}], float (&na)[{G}], float (&nb)[{G}]) {{"]
+
+    def ref(r):
+        if r < G:
+            return f"ca[{r}]"
+        if r < 2 * G:
+            return f"cb[{r - G}]"
+        if r < P.n_in:
+            return f"xr[{r - 2 * G}]"
+        return f"t{r}"
+
+    lines += emit_ops(P, ref)
+    for j in range(2 * G):
+        lines.append(f"  o[{j}] = {ref(P.outs[j])};")
+    for j in range(G):
+        lines.append(f"  na[{j}] = {ref(P.outs[2 * G + j])};")
+    for j in range(G):
+        lines.append(f"  nb[{j}] = {ref(P.outs[3 * G + j])};")
+    lines.append("}")
+    return "\n".join(lines)
+
+
+def emit_sort_cuda(P: Prog, n):
+    lines = [f"// sort of {n} values: {len(P.ops)} min/max ops",
+             f"__device__ __forceinline__ void median_sort{n}(const float (&x)[{n}], float (&y)[{n}]) {{"]
+
+    def ref(r):
+        return f"x[{r}]" if r < P.n_in else f"t{r}"
+
+    lines += emit_ops(P, ref)
+    for j in range(n):
+        lines.append(f"  y[{j}] = {ref(P.outs[j])};")
     lines.append("}")
     return "\n".join(lines)
 
@@ -214,7 +421,11 @@ def main():
     ap.add_argument('--ks', default=','.join(str(k) for k in range(3, 64, 2)))
     ap.add_argument('--gmax', type=int, default=12)
     ap.add_argument('--report', action='store_true')
+    ap.add_argument('--int-every', type=int, default=0,
+                    help='every n-th compare-exchange takes its max from integer adds on the bit patterns (0 = off)')
     args = ap.parse_args()
+    global INT_EVERY
+    INT_EVERY = args.int_every
     ks = [int(s) for s in args.ks.split(',')]
     chunks = ["// GENERATED by tools/gen_median_networks.py -- do not edit.",
               "// Sliding-median selection networks: G outputs of a width-K window from K+G-1 registers.",
@@ -230,6 +441,36 @@ def main():
         chunks.append(emit_cuda(P, K, G, f"median_group_k{K}"))
         chunks.append("")
         table.append((K, G))
+    # stateful double steps (K = 4G - 1) and the block sorts that start a line
+    # (only where the stateless group of the same K has the same G: the kernel finishes odd tiles with it)
+    step_ks = [(K, (K + 1) // 4) for K, G in table if K in (15, 31, 63) and G == (K + 1) // 4]
+    sorts_done = set()
+    for K, G in step_ks:
+        P = gen_step(K, G)
+        ok = verify_step(P, K, G)
+        print(f"K={K:3d}  stateful step G={G:2d}  ops={len(P.ops):5d}  per-output={len(P.ops) / (2 * G):6.1f}  verified={ok}",
+              file=sys.stderr)
+        if not ok:
+            raise SystemExit(f"step verification failed for K={K}")
+        if G not in sorts_done:
+            chunks.append(emit_sort_cuda(gen_sort(G), G))
+            chunks.append("")
+            sorts_done.add(G)
+        chunks.append(emit_step_cuda(P, K, G))
+        chunks.append("")
+    chunks.append("// MedianStep<K>: stateful walk along a line (2G outputs per step) where K = 4G - 1 has one")
+    chunks.append("template <int K> struct MedianStep { static constexpr bool available = false; static constexpr int G = 1; "
+                  "static constexpr int NRAW = 1; };")
+    for K, G in step_ks:
+        raw = step_raw_index(K, G)
+        chunks.append(f"template <> struct MedianStep<{K}> {{\n"
+                      f"  static constexpr bool available = true;\n  static constexpr int G = {G};\n"
+                      f"  static constexpr int NRAW = {len(raw)};\n"
+                      f"  static __device__ __forceinline__ int raw_pos(int n) {{ return n < {G - 1} ? n : (n < {2 * G - 2} ? n + 1 : n + {G + 1}); }}\n"
+                      f"  static __device__ __forceinline__ void sort(const float (&x)[{G}], float (&y)[{G}]) {{ median_sort{G}(x, y); }}\n"
+                      f"  static __device__ __forceinline__ void run(const float (&ca)[{G}], const float (&cb)[{G}], const float (&xr)[{len(raw)}], "
+                      f"float (&o)[{2 * G}], float (&na)[{G}], float (&nb)[{G}]) {{ median_step_k{K}(ca, cb, xr, o, na, nb); }}\n}};")
+    chunks.append("")
     chunks.append("template <int K> struct MedianGroup;   // G = outputs per group, run() = generated network")
     for K, G in table:
         chunks.append(f"template <> struct MedianGroup<{K}> {{ static constexpr int G = {G}; "
