@@ -180,6 +180,28 @@ int get_mel_plan(hpss_ctx* ctx, int sr, int n_fft, int n_mels, MelPlan** out) {
     if (ok) {
         HPSS_CUDA(cudaMalloc(&p->d_sweep, sizeof(int4) * rows));
         HPSS_CUDA(cudaMemcpy(p->d_sweep, sweep.data(), sizeof(int4) * rows, cudaMemcpyHostToDevice));
+        // emission counts (4 bits per row; padded with zeros to a multiple of 64 rows) and weights per row
+        const int rows_pad = (rows + 63) / 64 * 64;
+        std::vector<uint32_t> emit4(rows_pad / 8, 0u);
+        std::vector<float2> sw(rows_pad, make_float2(0.f, 0.f));
+        bool walk = true;
+        int prev = 0;
+        for (int f = 0; f < rows; ++f) {
+            const int cnt = sweep[f].x - prev;
+            prev = sweep[f].x;
+            if (cnt < 0 || cnt > 15) { walk = false; break; }
+            emit4[f / 8] |= (uint32_t)cnt << (4 * (f % 8));
+            float wa, wb;
+            memcpy(&wa, &sweep[f].y, 4); memcpy(&wb, &sweep[f].z, 4);
+            sw[f] = make_float2(wa, wb);
+        }
+        p->walkable = walk;
+        if (walk) {
+            HPSS_CUDA(cudaMalloc(&p->d_emit4, sizeof(uint32_t) * emit4.size()));
+            HPSS_CUDA(cudaMalloc(&p->d_sweep_w, sizeof(float2) * sw.size()));
+            HPSS_CUDA(cudaMemcpy(p->d_emit4, emit4.data(), sizeof(uint32_t) * emit4.size(), cudaMemcpyHostToDevice));
+            HPSS_CUDA(cudaMemcpy(p->d_sweep_w, sw.data(), sizeof(float2) * sw.size(), cudaMemcpyHostToDevice));
+        }
     }
     HPSS_CUDA(cudaMalloc(&p->d_w, sizeof(float) * w.size()));
     HPSS_CUDA(cudaMalloc(&p->d_band, sizeof(int2) * n_mels));
@@ -333,11 +355,18 @@ static int features_from_spec(hpss_ctx* ctx, const hpss_batch* b, const float* S
         // frequency median + soft masks + mel + log in one kernel when the kernel size has a generated
         // selection network and the mel basis can be swept with two running sums
         // (opt-in while it is not faster than the two separate kernels: HPSS_USE_FUSED=1)
-        static const bool use_fused = getenv("HPSS_USE_FUSED") && atoi(getenv("HPSS_USE_FUSED")) != 0;
+        static const int use_fused = getenv("HPSS_USE_FUSED") ? atoi(getenv("HPSS_USE_FUSED")) : 0;
         if (use_fused) {
-            rc = launch_median_freq_fused(ctx, b, S, harm, rows, p->l_perc, mp, is_log ? 1 : 0, p->amin, out,
-                                          clip ? clip_max : nullptr, st, &fused);
-            if (rc) return rc;
+            if (use_fused != 2 && mp) {   // register walk + mel sweep (k = 15, 31)
+                rc = launch_perc_mask_mel_walk(ctx, b, S, harm, rows, p->l_perc, mp, is_log ? 1 : 0, p->amin, out,
+                                               clip ? clip_max : nullptr, st, &fused);
+                if (rc) return rc;
+            }
+            if (!fused) {
+                rc = launch_median_freq_fused(ctx, b, S, harm, rows, p->l_perc, mp, is_log ? 1 : 0, p->amin, out,
+                                              clip ? clip_max : nullptr, st, &fused);
+                if (rc) return rc;
+            }
         }
         if (!fused) {
             rc = launch_median(ctx, b, S, rows, p->l_perc, false, perc, st);
@@ -457,7 +486,7 @@ int hpss_ctx_destroy(hpss_ctx* ctx) {
         cudaFree(kv.second->d_window); cudaFree(kv.second->d_tw_half); cudaFree(kv.second->d_tw_full);
         delete kv.second;
     }
-    for (auto& kv : ctx->mel_plans) { cudaFree(kv.second->d_w); cudaFree(kv.second->d_band); if (kv.second->d_sweep) cudaFree(kv.second->d_sweep); delete kv.second; }
+    for (auto& kv : ctx->mel_plans) { cudaFree(kv.second->d_w); cudaFree(kv.second->d_band); if (kv.second->d_sweep) cudaFree(kv.second->d_sweep); if (kv.second->d_emit4) cudaFree(kv.second->d_emit4); if (kv.second->d_sweep_w) cudaFree(kv.second->d_sweep_w); delete kv.second; }
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->band_scratch) cudaFree(ctx->band_scratch);
     for (int i = 0; i < 2; ++i) {
@@ -632,7 +661,14 @@ int hpss_perc_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* 
         if (rc) return rc;
     }
     bool handled = false;
-    int rc = launch_median_freq_fused(ctx, batch, S, harm, rows, k, mp, log_power, amin, out, clip_max,
+    int rc = HPSS_OK;
+    if (mp && !getenv("HPSS_NO_WALK")) {
+        rc = launch_perc_mask_mel_walk(ctx, batch, S, harm, rows, k, mp, log_power, amin, out, clip_max,
+                                       (cudaStream_t)stream, &handled);
+        if (rc) return rc;
+    }
+    if (!handled)
+        rc = launch_median_freq_fused(ctx, batch, S, harm, rows, k, mp, log_power, amin, out, clip_max,
                                       (cudaStream_t)stream, &handled);
     if (rc) return rc;
     if (!handled) {

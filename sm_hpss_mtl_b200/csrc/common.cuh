@@ -52,6 +52,11 @@ struct MelPlan {
     // sweep along f keep only two running sums per stream (valid when <= 2 ordered filters overlap)
     int4* d_sweep = nullptr;
     bool sweepable = false;
+    // the same sweep split for the fused walk kernel: filters finishing before row f (4 bits per row, 8 rows
+    // per word) and the two weights of row f; valid when no row finishes more than 15 filters
+    uint32_t* d_emit4 = nullptr;
+    float2* d_sweep_w = nullptr;
+    bool walkable = false;
 };
 
 }  // namespace hpss
@@ -121,6 +126,11 @@ int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const fl
 int launch_median_freq_fused(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, int rows, int k,
                              const MelPlan* mel, int log_power, float amin, float* out, uint32_t* clip_max,
                              cudaStream_t st, bool* handled);
+int launch_median_freq_walk(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, int k, float* out,
+                            cudaStream_t st, bool* handled);
+int launch_perc_mask_mel_walk(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, int rows, int k,
+                              const MelPlan* mel, int log_power, float amin, float* out, uint32_t* clip_max,
+                              cudaStream_t st, bool* handled);
 int launch_mel_bands(const float* mel, int n_mels, int rows, int2* band, cudaStream_t st);
 int launch_topdb(hpss_ctx* ctx, const hpss_batch* b, float* out, int rows_per_stream, int n_streams,
                  const uint32_t* clip_max, float top_db, cudaStream_t st);

@@ -764,6 +764,14 @@ int launch_median(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, 
         HPSS_CUDA(cudaMemcpyAsync(out, S, sizeof(float) * (size_t)rows * total_frames, cudaMemcpyDeviceToDevice, st));
         return HPSS_OK;
     }
+    if (!time_axis) {   // register walk (no shared-memory staging) where k has a stateful step network
+        static const bool no_walk = getenv("HPSS_NO_WALK") != nullptr;   // development knob
+        bool handled = false;
+        if (!no_walk) {
+            const int rc = launch_median_freq_walk(ctx, b, S, rows, k, out, st, &handled);
+            if (rc || handled) return rc;
+        }
+    }
 #define HPSS_DISPATCH_K(KK)                                                                                   \
     if (k == KK) {                                                                                            \
         return time_axis ? launch_fast<KK, true>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines,      \
