@@ -183,7 +183,7 @@ int get_mel_plan(hpss_ctx* ctx, int sr, int n_fft, int n_mels, MelPlan** out) {
         // emission counts (4 bits per row; padded with zeros to a multiple of 64 rows) and weights per row
         const int rows_pad = (rows + 63) / 64 * 64;
         std::vector<uint32_t> emit4(rows_pad / 8, 0u);
-        std::vector<float2> sw(rows_pad, make_float2(0.f, 0.f));
+        std::vector<float2> sw(rows_pad + 1, make_float2(0.f, 0.f));   // the sweep reads one row ahead
         bool walk = true;
         int prev = 0;
         for (int f = 0; f < rows; ++f) {

@@ -63,10 +63,11 @@ median_freq_walk_kernel(WalkArgs a, const int64_t* __restrict__ frame_off, const
     }
     const int64_t in_base = (int64_t)rows * fo + (gf - fo);
     const float* col = a.S + in_base;
+    const int Ti = (int)T;                     // row pitch of this lane's clip (32-bit: one IMAD.WIDE per address)
     // S[f] of this lane's frame, f reflected into [0, rows) (warp-uniform index)
     auto ld = [&](int f) -> float {
         const int fr = reflect_idx(f, rows);
-        return valid ? __ldg(col + (int64_t)fr * T) : 0.f;
+        return valid ? __ldg(col + (int64_t)fr * Ti) : 0.f;
     };
 
     // ---- FUSED state (mel sweep of K3)
@@ -78,6 +79,9 @@ median_freq_walk_kernel(WalkArgs a, const int64_t* __restrict__ frame_off, const
         op = oh + (int64_t)a.n_mels * T;
     }
     float* pcol = FUSED ? nullptr : a.perc + in_base;
+    // per-warp scratch of the fused variant: the masked values of one step, [2][2G][32]
+    __shared__ float s_scr[FUSED ? kWalkWarps * 4 * G * 32 : 1];
+    float* scr = s_scr + (FUSED ? warp * 4 * G * 32 : 0);
     float aH = 0.f, aP = 0.f, bH = 0.f, bP = 0.f;
     float vmaxH = -INFINITY, vmaxP = -INFINITY;
     int cur = 0;
@@ -118,16 +122,20 @@ median_freq_walk_kernel(WalkArgs a, const int64_t* __restrict__ frame_off, const
 #pragma unroll 1
     for (int s = 0; s < nsteps; ++s) {
         const int base = 2 * G * s;
+        const bool interior = base + 6 * G - 2 < rows;    // no reflection in this step's loads (warp-uniform)
         // harmonic medians at this step's output rows: in flight while the selection network runs
         float hv[2 * G];
         uint32_t em[(2 * G + 7) / 8];
         if (FUSED) {
 #pragma unroll
             for (int i = 0; i < (2 * G + 7) / 8; ++i) em[i] = __ldg(a.emit4 + (base >> 3) + i);
+            const float* hp = hcol + (int64_t)base * Ti;
+            if (interior) {
 #pragma unroll
-            for (int j = 0; j < 2 * G; ++j) {
-                const int f = base + j;
-                hv[j] = (valid && f < rows) ? __ldg(hcol + (int64_t)f * T) : 0.f;
+                for (int j = 0; j < 2 * G; ++j) hv[j] = valid ? __ldg(hp + (int64_t)j * Ti) : 0.f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2 * G; ++j) hv[j] = (valid && base + j < rows) ? __ldg(hp + (int64_t)j * Ti) : 0.f;
             }
         }
         float xr[NR], o[2 * G], na[G], nb[G];
@@ -140,42 +148,65 @@ median_freq_walk_kernel(WalkArgs a, const int64_t* __restrict__ frame_off, const
         for (int i = 0; i < G; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
         // the 2G new input rows of the next step: in flight during the stores / the mask and mel phase
         float nn[2 * G];
-        if (s + 1 < nsteps) {
+        if (interior) {
+            const float* np = col + (int64_t)(base + 4 * G - 1) * Ti;
+#pragma unroll
+            for (int i = 0; i < 2 * G; ++i) nn[i] = valid ? __ldg(np + (int64_t)i * Ti) : 0.f;
+        } else if (s + 1 < nsteps) {
 #pragma unroll
             for (int i = 0; i < 2 * G; ++i) nn[i] = ld(base + 4 * G - 1 + i);
         }
 
         if (!FUSED) {
             if (valid) {
-                float* dst = pcol + (int64_t)base * T;
+                float* dst = pcol + (int64_t)base * Ti;
+                if (interior) {
 #pragma unroll
-                for (int j = 0; j < 2 * G; ++j)
-                    if (base + j < rows) dst[(int64_t)j * T] = o[j];
+                    for (int j = 0; j < 2 * G; ++j) dst[(int64_t)j * Ti] = o[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 2 * G; ++j)
+                        if (base + j < rows) dst[(int64_t)j * Ti] = o[j];
+                }
             }
         } else {
             // S at the output rows = the window centres x[HALO + j] = c1[0..G-1], hi[0..G-2], nw[0]
-            float sc[2 * G], Hm[2 * G], Pm[2 * G];
+            {
+                float sc[2 * G], Hm[2 * G], Pm[2 * G];
 #pragma unroll
-            for (int j = 0; j < G; ++j) sc[j] = c1[j];
+                for (int j = 0; j < G; ++j) sc[j] = c1[j];
 #pragma unroll
-            for (int j = 0; j < G - 1; ++j) sc[G + j] = hi[j];
-            sc[2 * G - 1] = nw[0];
-            softmask_batch<2 * G>(sc, hv, o, Hm, Pm);
-            // mel sweep: weights of all 2G rows first (independent loads), then per row the filters that finish
-            // before it (count from the emission table: no load sits in front of a branch) and four FMAs
-            float2 w[2 * G];
+                for (int j = 0; j < G - 1; ++j) sc[G + j] = hi[j];
+                sc[2 * G - 1] = nw[0];
+                softmask_batch<2 * G>(sc, hv, o, Hm, Pm);
 #pragma unroll
-            for (int j = 0; j < 2 * G; ++j) w[j] = __ldg(a.sweep_w + base + j);      // table is zero padded
-#pragma unroll
+                for (int j = 0; j < 2 * G; ++j) {
+                    scr[j * 32 + lane] = Hm[j];
+                    scr[(2 * G + j) * 32 + lane] = Pm[j];
+                }
+            }
+            __syncwarp();
+            // mel sweep, one row per iteration of a rolled loop (its body exists once in the code): the filters
+            // that finish before the row (count from the emission table: no load sits in front of a branch),
+            // then four FMAs; the next row's weights and masked values are fetched one iteration ahead
+            float2 wn = __ldg(a.sweep_w + base);                                    // table is zero padded
+            float hnx = scr[lane], pnx = scr[2 * G * 32 + lane];
+#pragma unroll 1
             for (int j = 0; j < 2 * G; ++j) {
-                int n = (int)((em[j / 8] >> (4 * (j % 8))) & 15u);                   // warp-uniform
+                const float2 w = wn;
+                const float H = hnx, P = pnx;
+                wn = __ldg(a.sweep_w + base + j + 1);
+                hnx = scr[((j + 1) & (2 * G - 1)) * 32 + lane];
+                pnx = scr[(2 * G + ((j + 1) & (2 * G - 1))) * 32 + lane];
+                int n = (int)((em[(2 * G > 8 && j >= 8) ? 1 : 0] >> (4 * (j & 7))) & 15u);    // warp-uniform
 #pragma unroll 1
                 for (; n > 0; --n) emit();
-                aH = fmaf(w[j].x, Hm[j], aH);
-                aP = fmaf(w[j].x, Pm[j], aP);
-                bH = fmaf(w[j].y, Hm[j], bH);
-                bP = fmaf(w[j].y, Pm[j], bP);
+                aH = fmaf(w.x, H, aH);
+                aP = fmaf(w.x, P, aP);
+                bH = fmaf(w.y, H, bH);
+                bP = fmaf(w.y, P, bP);
             }
+            __syncwarp();
         }
 
         // carry the raw values the next step reads again: x'[i] = x[i + 2G]
