@@ -44,6 +44,16 @@ def env_int(name, default):
         return default
 
 
+def measured_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/r1_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return int(t["read"]) + int(t["write"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -54,7 +64,7 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -67,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -108,7 +118,8 @@ def run_reference(args):
         return 0            # one CPU arm per box: the other ranks exit without work
     from oracle.cpu_baseline import CpuArm, usable_cores
     cores = usable_cores()
-    arm = CpuArm(CFG, cores=cores, n_per_worker=args.cpu_clips_per_core)
+    per_core = args.cpu_clips_per_core or 64
+    arm = CpuArm(CFG, cores=cores, n_per_worker=per_core)
     for _ in range(max(args.warmup, 1)):
         arm.step()
     times = [arm.step() for _ in range(args.steps)]
@@ -117,7 +128,7 @@ def run_reference(args):
     total = sum(times)
     value = audio_s * args.steps / total
     sample = (f"{arm.clips_per_step} of the 4096 clips per step ({cores} single-threaded workers x "
-              f"{args.cpu_clips_per_core} clips), oracle = librosa algorithm on scipy.ndimage/numpy.fft/np.dot")
+              f"{per_core} clips), oracle = librosa algorithm on scipy.ndimage/numpy.fft/np.dot")
     line = {
         "impl": "reference", "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -134,7 +145,7 @@ def run_reference(args):
 def cpu_baseline_block(args):
     from oracle.cpu_baseline import CpuArm, usable_cores
     cores = usable_cores()
-    arm = CpuArm(CFG, cores=cores, n_per_worker=args.cpu_clips_per_core)
+    arm = CpuArm(CFG, cores=cores, n_per_worker=args.cpu_clips_per_core or 256)
     arm.step()
     reps = 2
     t = sum(arm.step() for _ in range(reps))
@@ -274,9 +285,12 @@ def run_gpu(args):
                            "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)})
         dom = max(stages, key=lambda s: s["ms"])
         roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": dom["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
-                    "note": "median kernels are bound by the ALU pipe (FMNMX selection network), HBM is the "
-                            "secondary bound; per-stage numbers in 'stages'"}
+                    "unit": "GB/s", "frac": dom["frac_of_hbm_peak"], "traffic": measured_traffic(dom["kernel"]),
+                    "algorithmic_bytes": dom["algorithmic_bytes_per_frame"] * frames, "peak_source": peak_src,
+                    "traffic_source": "profiles/r1_traffic.json (ncu --set full of the same kernels, bytes per launch)",
+                    "note": "the two median kernels are bound by the ALU pipe (half-rate FMNMX selection networks: "
+                            "profiles/README.md), HBM is their secondary bound; K1/K3/K3b+K5 are the HBM-side "
+                            "stages; per-stage numbers in 'stages'"}
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
@@ -311,7 +325,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=CFG["n_clips"], help="clips per GPU (default: the named 4096)")
-    ap.add_argument("--cpu-clips-per-core", type=int, default=16)
+    ap.add_argument("--cpu-clips-per-core", type=int, default=0,
+                    help="clips per worker and pass of the CPU legs (default: 256 for cpu_baseline = the whole 4096-clip "
+                         "workload on 16 cores, ~15 s; 64 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
