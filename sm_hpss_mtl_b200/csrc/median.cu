@@ -163,9 +163,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // loader: fill one tile asynchronously
 // (loader warp `lw` of kLoaderWarps takes every kLoaderWarps-th row / position)
+struct FillCache {   // time axis, uniform batch: reflected source offsets of this lane's tile positions
+    static constexpr int kChunks = 8;
+    int p0 = -1, n0 = -1;
+    int off[kChunks];
+};
+
 template <bool TIME_AXIS>
 __device__ __forceinline__ void tile_fill_async(uint32_t sm_base, const float* __restrict__ S, const LineInfo& li,
-                                                int lane, int lw, int p0, int halo, int span, int lstride) {
+                                                int lane, int lw, int p0, int halo, int span, int lstride, FillCache& fc) {
     if (TIME_AXIS) {
         // lanes sweep positions of one row at a time (coalesced); reflected source indices are
         // computed once per lane when all 32 rows have the same length (uniform batch)
@@ -173,15 +179,24 @@ __device__ __forceinline__ void tile_fill_async(uint32_t sm_base, const float* _
         const bool uniform = __all_sync(0xffffffffu, li.n == n0);
         if (uniform) {
             if (n0 == 0 || p0 >= n0) return;
-            // equal lengths => consecutive lines are exactly n0 elements apart, also across clips
-            const float* row0 = S + __shfl_sync(0xffffffffu, li.base, 0) + (int64_t)lw * n0;
+            // equal lengths => consecutive lines are exactly n0 elements apart, also across clips.
+            // The reflected source offsets of this lane's positions depend on (p0, n0) only: they are kept in
+            // registers from tile to tile, so a row costs one address add per 128-byte copy.
+            constexpr int NCH = FillCache::kChunks;             // span = TT + K - 1 <= 16 * 12 + 62 = 254 < 8 * 32
+            if (fc.p0 != p0 || fc.n0 != n0) {
+                fc.p0 = p0; fc.n0 = n0;
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) fc.off[q] = reflect_idx(p0 - halo + lane + 32 * q, n0);
+            }
+            const float* rowp = S + __shfl_sync(0xffffffffu, li.base, 0) + (int64_t)lw * n0;
+            uint32_t drow = sm_base + 4u * (uint32_t)(lw * lstride + lane);
             const uint32_t dstep = 4u * (uint32_t)(kLoaderWarps * lstride);
-            const int sstep = kLoaderWarps * n0;
-            for (int pos = lane; pos < span; pos += 32) {
-                const float* src = row0 + reflect_idx(p0 - halo + pos, n0);
-                uint32_t d = sm_base + 4u * (uint32_t)(pos + lw * lstride);
-#pragma unroll 8
-                for (int r = lw; r < 32; r += kLoaderWarps, d += dstep, src += sstep) cp_async4(d, src);
+            const int64_t sstep = (int64_t)kLoaderWarps * n0;
+#pragma unroll 2
+            for (int r = lw; r < 32; r += kLoaderWarps, drow += dstep, rowp += sstep) {
+#pragma unroll
+                for (int q = 0; q < NCH; ++q)
+                    if (lane + 32 * q < span) cp_async4(drow + 128u * q, rowp + fc.off[q]);
             }
         } else {
             for (int r = lw; r < 32; r += kLoaderWarps) {
@@ -249,6 +264,7 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
     if (warp >= kComputeWarps) {
         // ===== loader warps =====
         const int lw = warp - kComputeWarps;
+        FillCache fc;
         for (int64_t n = 0; n < my_items; ++n) {
             const int b = (int)(n % NB);
             const uint32_t use = (uint32_t)(n / NB);
@@ -257,7 +273,7 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
             const int p0 = (int)(item - lb * n_ptiles) * TT;
             const LineInfo li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane);
             if (use > 0) mbar_wait(empty0 + 8u * b, (use - 1) & 1u);
-            tile_fill_async<TIME_AXIS>(smem_u32(smem + (size_t)b * tile_floats), S, li, lane, lw, p0, HALO, span, lstride);
+            tile_fill_async<TIME_AXIS>(smem_u32(smem + (size_t)b * tile_floats), S, li, lane, lw, p0, HALO, span, lstride, fc);
             cp_async_arrive(full0 + 8u * b);
         }
     } else {
