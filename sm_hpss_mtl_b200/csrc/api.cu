@@ -378,6 +378,7 @@ static int features_from_spec(hpss_ctx* ctx, const hpss_batch* b, const float* S
         rc = launch_mask_mel(ctx, b, S, ns == 2 ? harm : nullptr, ns == 2 ? perc : nullptr, rows,
                              mp ? mp->d_w : nullptr, mp ? mp->d_band : nullptr,
                              (mp && mp->sweepable && !getenv("HPSS_NO_SWEEP")) ? mp->d_sweep : nullptr,
+                             (mp && mp->walkable) ? mp->d_emit4 : nullptr, (mp && mp->walkable) ? mp->d_sweep_w : nullptr,
                              mp ? mp->n_mels : 0, pre_square,
                              is_log ? 1 : 0, p->amin, out, clip ? clip_max : nullptr, st);
         if (rc) return rc;
@@ -629,8 +630,8 @@ int hpss_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* S, co
         int rc = launch_mel_bands(mel, n_mels, rows, band, st);
         if (rc) return rc;
     }
-    return launch_mask_mel(ctx, batch, S, harm, perc, rows, mel, band, nullptr, n_mels, pre_square, log_power, amin,
-                           out, clip_max, st);
+    return launch_mask_mel(ctx, batch, S, harm, perc, rows, mel, band, nullptr, nullptr, nullptr, n_mels, pre_square,
+                           log_power, amin, out, clip_max, st);
 }
 
 int hpss_mask_mel_log_sr(hpss_ctx* ctx, const hpss_batch* batch, const float* S, const float* harm, const float* perc,
@@ -645,7 +646,8 @@ int hpss_mask_mel_log_sr(hpss_ctx* ctx, const hpss_batch* batch, const float* S,
     int rc = get_mel_plan(ctx, mel_sr, 2 * (rows - 1), n_mels, &mp);
     if (rc) return rc;
     return launch_mask_mel(ctx, batch, S, harm, perc, rows, mp->d_w, mp->d_band, mp->sweepable ? mp->d_sweep : nullptr,
-                           n_mels, pre_square, log_power, amin, out, clip_max, (cudaStream_t)stream);
+                           mp->walkable ? mp->d_emit4 : nullptr, mp->walkable ? mp->d_sweep_w : nullptr, n_mels,
+                           pre_square, log_power, amin, out, clip_max, (cudaStream_t)stream);
 }
 
 int hpss_perc_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* S, const float* harm, int32_t rows,

@@ -121,8 +121,8 @@ int launch_median(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, 
                   float* out, cudaStream_t st);
 int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm,
                     const float* perc, int rows, const float* mel, const int2* band, const int4* sweep,
-                    int n_mels, int pre_square, int log_power, float amin, float* out, uint32_t* clip_max,
-                    cudaStream_t st);
+                    const uint32_t* emit4, const float2* sweep_w, int n_mels, int pre_square, int log_power,
+                    float amin, float* out, uint32_t* clip_max, cudaStream_t st);
 int launch_median_freq_fused(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, int rows, int k,
                              const MelPlan* mel, int log_power, float amin, float* out, uint32_t* clip_max,
                              cudaStream_t st, bool* handled);

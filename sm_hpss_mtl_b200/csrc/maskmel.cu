@@ -281,6 +281,78 @@ mask_mel_sweep_kernel(const float* __restrict__ S, const float* __restrict__ har
     }
 }
 
+// Same sweep with the split tables of the mel plan (emission counts, 4 bits per row + the two weights per row):
+// no load sits in front of a branch, the U soft masks of an iteration are one basic block of interleaved
+// chains (softmask_batch) and power_to_db is resolved at compile time.  Bit-identical to the kernel above.
+template <int U, int LOGP>
+__global__ void __launch_bounds__(kThreads)
+mask_mel_sweep2_kernel(const float* __restrict__ S, const float* __restrict__ harm, const float* __restrict__ perc,
+                       const int64_t* __restrict__ frame_off, const int32_t* __restrict__ block_clip,
+                       int64_t total_frames, int rows, const uint32_t* __restrict__ emit4,
+                       const float2* __restrict__ sweep_w, int n_mels, float amin, float* __restrict__ out,
+                       uint32_t* __restrict__ clip_max) {
+    static_assert(8 % U == 0, "U rows never straddle a word of the emission table");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t g0 = ((int64_t)blockIdx.x * kWarps + warp) * 32;
+    if (g0 >= total_frames) return;
+    const FrameLane fl = frame_lane(frame_off, block_clip, total_frames, g0 + lane, rows, 2 * n_mels);
+    const int T = fl.T;
+    const float* sp = S + fl.in_base;
+    const float* hp = harm + fl.in_base;
+    const float* pp = perc + fl.in_base;
+    float* oh = out + fl.out_base;
+    float* op = oh + (int64_t)n_mels * T;
+    float aH = 0.f, aP = 0.f, bH = 0.f, bP = 0.f;     // running sums of filters cur, cur + 1
+    float vmaxH = -INFINITY, vmaxP = -INFINITY;
+    int cur = 0;
+    auto emit = [&]() {
+        const float vH = post_value(aH, LOGP, amin);
+        const float vP = post_value(aP, LOGP, amin);
+        if (fl.valid) { *oh = vH; *op = vP; }
+        oh += T; op += T;
+        vmaxH = fmaxf(vmaxH, vH);
+        vmaxP = fmaxf(vmaxP, vP);
+        aH = bH; aP = bP; bH = 0.f; bP = 0.f;
+        ++cur;
+    };
+    const int rows_u = (rows + U - 1) / U * U;         // the tables are zero padded to a multiple of 64 rows
+#pragma unroll 1
+    for (int f0 = 0; f0 < rows_u; f0 += U) {
+        float sv[U], hv[U], pv[U];
+        float2 w[U];
+        const uint32_t em = __ldg(emit4 + (f0 >> 3)) >> (4 * (f0 & 7));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            sv[u] = 0.f; hv[u] = 0.f; pv[u] = 0.f;
+            if (fl.valid && f0 + u < rows) {
+                sv[u] = __ldg(sp + (int64_t)u * T);
+                hv[u] = __ldg(hp + (int64_t)u * T);
+                pv[u] = __ldg(pp + (int64_t)u * T);
+            }
+            w[u] = __ldg(sweep_w + f0 + u);
+        }
+        sp += (int64_t)U * T; hp += (int64_t)U * T; pp += (int64_t)U * T;
+        float H[U], P[U];
+        softmask_batch<U>(sv, hv, pv, H, P);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            int n = (int)((em >> (4 * u)) & 15u);          // warp-uniform
+#pragma unroll 1
+            for (; n > 0; --n) emit();
+            aH = fmaf(w[u].x, H[u], aH);
+            aP = fmaf(w[u].x, P[u], aP);
+            bH = fmaf(w[u].y, H[u], bH);
+            bP = fmaf(w[u].y, P[u], bP);
+        }
+    }
+#pragma unroll 1
+    while (cur < n_mels) emit();                       // filters above the last frequency row
+    if (clip_max != nullptr) {
+        publish_max(clip_max, 2, 0, fl.valid, fl.clip, vmaxH);
+        publish_max(clip_max, 2, 1, fl.valid, fl.clip, vmaxP);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 topdb_kernel(float* __restrict__ out, const int64_t* __restrict__ frame_off, const int32_t* __restrict__ block_clip, int64_t total_frames,
              int rows_per_stream, int n_streams, const uint32_t* __restrict__ clip_max, float top_db) {
@@ -320,13 +392,26 @@ int launch_mel_bands(const float* mel, int n_mels, int rows, int2* band, cudaStr
 }
 
 int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, const float* perc,
-                    int rows, const float* mel, const int2* band, const int4* sweep, int n_mels, int pre_square,
-                    int log_power, float amin, float* out, uint32_t* clip_max, cudaStream_t st) {
+                    int rows, const float* mel, const int2* band, const int4* sweep, const uint32_t* emit4,
+                    const float2* sweep_w, int n_mels, int pre_square, int log_power, float amin, float* out,
+                    uint32_t* clip_max, cudaStream_t st) {
     const int64_t total = b->frame_off[b->n_clips];
     const bool hpss_mode = harm != nullptr;
     const int ns = hpss_mode ? 2 : 1;
     if (clip_max) HPSS_CUDA(cudaMemsetAsync(clip_max, 0, sizeof(uint32_t) * (size_t)ns * b->n_clips, st));
     if (total == 0) return HPSS_OK;
+    if (hpss_mode && mel && emit4 && sweep_w && (log_power == 0 || log_power == 1) && !getenv("HPSS_SWEEP1")) {
+        const int64_t n_warps = (total + 31) / 32;
+        const unsigned grid = (unsigned)((n_warps + kWarps - 1) / kWarps);
+        if (log_power)
+            mask_mel_sweep2_kernel<4, 1><<<grid, kThreads, 0, st>>>(S, harm, perc, b->d_frame_off, b->d_block_clip, total, rows,
+                                                                    emit4, sweep_w, n_mels, amin, out, clip_max);
+        else
+            mask_mel_sweep2_kernel<4, 0><<<grid, kThreads, 0, st>>>(S, harm, perc, b->d_frame_off, b->d_block_clip, total, rows,
+                                                                    emit4, sweep_w, n_mels, amin, out, clip_max);
+        HPSS_LAUNCHED("mask_mel_sweep2_kernel");
+        return HPSS_OK;
+    }
     if (hpss_mode && mel && sweep) {
         const int64_t n_warps = (total + 31) / 32;
         const unsigned grid = (unsigned)((n_warps + kWarps - 1) / kWarps);
