@@ -10,6 +10,9 @@ namespace hpss {
 
 namespace {
 
+#ifndef HPSS_MOM_MINB
+#define HPSS_MOM_MINB 3
+#endif
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
@@ -76,7 +79,7 @@ __device__ __forceinline__ void block_fold(float* row, int n, int cls, float thr
 }
 
 template <int MAXC, bool CLIP>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, HPSS_MOM_MINB)
 moments_kernel(float* __restrict__ feat, const int64_t* __restrict__ frame_off,
                const int32_t* __restrict__ block_clip, int n_clips, int64_t total_frames, int64_t chunk_frames,
                int D, const int32_t* __restrict__ clip_class, int n_classes, double* __restrict__ g_sum,
@@ -99,29 +102,46 @@ moments_kernel(float* __restrict__ feat, const int64_t* __restrict__ frame_off,
         const int64_t g1 = min(total_frames, g0 + chunk_frames);
         int c = find_clip_hint(frame_off, block_clip, g0);
         int64_t fo = __ldg(frame_off + c), fe = __ldg(frame_off + c + 1);
-        while (g0 < g1) {
-            while (fe <= g0) { ++c; fo = fe; fe = __ldg(frame_off + c + 1); }   // next non-empty clip
-            const int T = (int)(fe - fo);
-            const int len = (int)(min(g1, fe) - g0);
-            const int cls = __ldg(clip_class + c);
-            float thr0 = -INFINITY, thr1 = -INFINITY;
-            if (CLIP) {
-                const uint32_t* cm = clip_max + (size_t)n_streams * c;
-                thr0 = ordered_to_float(__ldg(cm + st0)) - top_db;
-                thr1 = ordered_to_float(__ldg(cm + st1)) - top_db;
-            }
-            float* r0 = feat + (int64_t)D * fo + (int64_t)d0 * T + (g0 - fo);
-            float* r1 = r0 + (int64_t)half * T;
-            for (int t0 = 0; t0 < len; t0 += 128) {
-                const int n = min(128, len - t0);
-                float x0[4], x1[4];
-                block_load<CLIP>(r0 + t0, n, lane, x0);
-                block_load<CLIP>(r1 + t0, two ? n : 0, lane, x1);
-                block_fold<MAXC, CLIP>(r0 + t0, n, cls, thr0, lane, x0, s0, q0, bad);
-                block_fold<MAXC, CLIP>(r1 + t0, two ? n : 0, cls, thr1, lane, x1, s1, q1, bad);
-            }
-            g0 += len;
+        // Software pipeline over 128-frame blocks: block B's offsets, class and thresholds are looked up and
+        // its eight loads issued before block A is folded, so neither the metadata chain nor the HBM latency
+        // of the next block is exposed.
+        struct Blk { float* r0; float* r1; int n; int cls; float thr0, thr1; };
+#define HPSS_NEXT_BLOCK(B)                                                                                   \
+        do {                                                                                                 \
+            (B).n = 0; (B).r0 = feat; (B).r1 = feat; (B).cls = 0; (B).thr0 = -INFINITY; (B).thr1 = -INFINITY; \
+            if (g0 < g1) {                                                                                   \
+                while (fe <= g0) { ++c; fo = fe; fe = __ldg(frame_off + c + 1); }   /* next non-empty clip */ \
+                const int T_ = (int)(fe - fo);                                                               \
+                (B).n = (int)(min(min(g1, fe), g0 + 128) - g0);                                              \
+                (B).cls = __ldg(clip_class + c);                                                             \
+                if (CLIP) {                                                                                  \
+                    const uint32_t* cm_ = clip_max + (size_t)n_streams * c;                                  \
+                    (B).thr0 = ordered_to_float(__ldg(cm_ + st0)) - top_db;                                  \
+                    (B).thr1 = ordered_to_float(__ldg(cm_ + st1)) - top_db;                                  \
+                }                                                                                            \
+                (B).r0 = feat + (int64_t)D * fo + (int64_t)d0 * T_ + (g0 - fo);                              \
+                (B).r1 = (B).r0 + (int64_t)half * T_;                                                        \
+                g0 += (B).n;                                                                                 \
+            }                                                                                                \
+        } while (0)
+        Blk A;
+        float xa0[4], xa1[4];
+        HPSS_NEXT_BLOCK(A);
+        block_load<CLIP>(A.r0, A.n, lane, xa0);
+        block_load<CLIP>(A.r1, two ? A.n : 0, lane, xa1);
+        while (A.n > 0) {
+            Blk B;
+            float xb0[4], xb1[4];
+            HPSS_NEXT_BLOCK(B);
+            block_load<CLIP>(B.r0, B.n, lane, xb0);
+            block_load<CLIP>(B.r1, two ? B.n : 0, lane, xb1);
+            block_fold<MAXC, CLIP>(A.r0, A.n, A.cls, A.thr0, lane, xa0, s0, q0, bad);
+            block_fold<MAXC, CLIP>(A.r1, two ? A.n : 0, A.cls, A.thr1, lane, xa1, s1, q1, bad);
+            A = B;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { xa0[u] = xb0[u]; xa1[u] = xb1[u]; }
         }
+#undef HPSS_NEXT_BLOCK
         q0 = warp_sum(q0);
         q1 = warp_sum(q1);
 #pragma unroll
