@@ -233,6 +233,68 @@ median_freq_walk_kernel(WalkArgs a, const int64_t* __restrict__ frame_off, const
     }
 }
 
+// The same register walk for every other kernel size with a generated (stateless) group network: the K + G - 1
+// inputs of a group live in registers, a group produces G outputs, the window then moves up by G rows (K - 1
+// register moves, G coalesced loads prefetched during the previous network).
+template <int K>
+__global__ void __launch_bounds__(kWalkWarps * 32, K > 43 ? 3 : 4)
+median_freq_walk_group_kernel(const float* __restrict__ S, float* __restrict__ perc, const int64_t* __restrict__ frame_off,
+                              const int32_t* __restrict__ block_clip, int64_t total_frames, int rows) {
+    constexpr int G = MedianGroup<K>::G;
+    constexpr int HALO = K / 2;
+    constexpr int NX = K + G - 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t g0 = ((int64_t)blockIdx.x * kWalkWarps + warp) * 32;
+    if (g0 >= total_frames) return;
+    const int64_t gf = g0 + lane;
+    const bool valid = gf < total_frames;
+    int64_t fo = 0;
+    int Ti = 1;
+    if (valid) {
+        const int clip = find_clip_hint(frame_off, block_clip, gf);
+        fo = __ldg(frame_off + clip);
+        Ti = (int)(__ldg(frame_off + clip + 1) - fo);
+    }
+    const int64_t in_base = (int64_t)rows * fo + (gf - fo);
+    const float* col = S + in_base;
+    float* pcol = perc + in_base;
+    auto ld = [&](int f) -> float {
+        const int fr = reflect_idx(f, rows);
+        return valid ? __ldg(col + (int64_t)fr * Ti) : 0.f;
+    };
+    float x[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = ld(-HALO + i);
+    const int ngroups = (rows + G - 1) / G;
+#pragma unroll 1
+    for (int g = 0; g < ngroups; ++g) {
+        const int base = g * G;
+        const int fnew = base + HALO + G;                   // first new row of the next group
+        const bool interior = fnew + G - 1 < rows;          // warp-uniform: no reflection in the next loads
+        float nn[G];
+        if (interior) {
+            const float* np = col + (int64_t)fnew * Ti;
+#pragma unroll
+            for (int j = 0; j < G; ++j) nn[j] = valid ? __ldg(np + (int64_t)j * Ti) : 0.f;
+        } else if (g + 1 < ngroups) {
+#pragma unroll
+            for (int j = 0; j < G; ++j) nn[j] = ld(fnew + j);
+        }
+        float o[G];
+        MedianGroup<K>::run(x, o);
+        if (valid) {
+            float* dst = pcol + (int64_t)base * Ti;
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                if (base + j < rows) dst[(int64_t)j * Ti] = o[j];
+        }
+#pragma unroll
+        for (int i = 0; i < K - 1; ++i) x[i] = x[i + G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) x[K - 1 + j] = nn[j];
+    }
+}
+
 template <int K, bool FUSED>
 int launch_walk(const hpss_batch* b, const WalkArgs& wa, int rows, int64_t total, cudaStream_t st) {
     const int64_t n_warps = (total + 31) / 32;
@@ -265,6 +327,19 @@ int launch_median_freq_walk(hpss_ctx* ctx, const hpss_batch* b, const float* S, 
     }
     HPSS_WALK_K(15) HPSS_WALK_K(31)
 #undef HPSS_WALK_K
+#define HPSS_WALK_GROUP_K(KK)                                                                                       \
+    if (k == KK) {                                                                                                  \
+        *handled = true;                                                                                            \
+        if (total == 0) return HPSS_OK;                                                                             \
+        const int64_t n_warps = (total + 31) / 32;                                                                  \
+        const unsigned grid = (unsigned)((n_warps + kWalkWarps - 1) / kWalkWarps);                                  \
+        median_freq_walk_group_kernel<KK><<<grid, kWalkWarps * 32, 0, st>>>(S, out, b->d_frame_off, b->d_block_clip, \
+                                                                            total, rows);                           \
+        HPSS_LAUNCHED("median_freq_walk_group_kernel");                                                             \
+        return HPSS_OK;                                                                                             \
+    }
+    HPSS_MEDIAN_FAST_KS(HPSS_WALK_GROUP_K)
+#undef HPSS_WALK_GROUP_K
     return HPSS_OK;
 }
 
