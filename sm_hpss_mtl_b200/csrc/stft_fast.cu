@@ -43,7 +43,7 @@ struct FastCfg {
     static_assert(HOP % 4 == 0 && NT % 32 == 0, "vector staging");
 };
 
-template <int NFFT, int HOP, int NA, int NB, int NT>
+template <int NFFT, int HOP, int NA, int NB, int NT, int MODE>
 __global__ void __launch_bounds__(NT)
 stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sample_off,
                  const int64_t* __restrict__ frame_off, const int2* __restrict__ tiles,
@@ -66,8 +66,11 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
     const int nf = min(C::TT, T - t0);
 
     // ---- stage tables and the sample segment
-    for (int i = tid; i < NFFT / 2; i += NT)
-        reinterpret_cast<float2*>(s_win)[i] = __ldg(reinterpret_cast<const float2*>(window) + i);
+    // window x 0.5 (exact): the spectrum buffer then holds Z/2 and the unpack needs no halving
+    for (int i = tid; i < NFFT / 2; i += NT) {
+        const float2 wv = __ldg(reinterpret_cast<const float2*>(window) + i);
+        reinterpret_cast<float2*>(s_win)[i] = make_float2(0.5f * wv.x, 0.5f * wv.y);
+    }
     for (int i = tid; i < N2; i += NT) s_twh[i] = __ldg(tw_half + i);
     for (int i = tid; i <= N2 / 2; i += NT) s_twf[i] = __ldg(tw_full + i);
     {
@@ -131,6 +134,7 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
             Dft<NB>::run(v);
 #pragma unroll
             for (int k2 = 0; k2 < NB; ++k2) z[NA * k2] = v[k2];
+            if (k1 == 0) z[N2] = v[0];          // Z[N2] = Z[0] (periodicity): the unpack reads Z[N2 - k] for k = 0 too
         }
     }
     __syncthreads();
@@ -141,29 +145,47 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
         const int F = N2 + 1;
         const float2* zrow = Z + fr * ZS;
         const int64_t base = (int64_t)F * fo + t0 + fr;
-        float* Sg = S + base;
-        float2* Cg = cplx ? cplx + base : nullptr;
-#pragma unroll 2
-        for (int k = g; k <= N2 / 2; k += G) {
-            const int k2 = N2 - k;
+        char* Sg = reinterpret_cast<char*>(S + base);
+        const int T4 = 4 * T;                              // row pitch in bytes: one IMAD.WIDE per address
+        // one bin pair: X[k] = E + W*O, X[N2-k] = conj(E - W*O), E = Z[k] + conj(Z[N2-k]), O = -i (Z[k] - conj(Z[N2-k]))
+        auto pair = [&](int k, float2& xa, float2& xb) {
             const float2 zk = zrow[k];
-            float2 zc = zrow[k == 0 ? 0 : k2];
-            zc.y = -zc.y;
-            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-            const float2 dd = make_float2(zk.x - zc.x, zk.y - zc.y);
-            const float2 o = make_float2(0.5f * dd.y, -0.5f * dd.x);
+            const float2 zc = zrow[N2 - k];
+            const float2 e = make_float2(zk.x + zc.x, zk.y - zc.y);
+            const float2 o = make_float2(zk.y + zc.y, zc.x - zk.x);
             const float2 w = s_twf[k];
             const float2 wo = make_float2(w.x * o.x - w.y * o.y, w.x * o.y + w.y * o.x);
-            const float2 xa = make_float2(e.x + wo.x, e.y + wo.y);      // X[k]
-            const float2 xb = make_float2(e.x - wo.x, wo.y - e.y);      // X[N2-k] = conj(E - W*O)
-            const float pa = xa.x * xa.x + xa.y * xa.y;
-            const float pb = xb.x * xb.x + xb.y * xb.y;
-            const int64_t ga = (int64_t)k * T, gb = (int64_t)k2 * T;
-            Sg[ga] = power ? pa : fast_sqrt(pa);
-            if (Cg) Cg[ga] = xa;
-            if (k2 != k) {
-                Sg[gb] = power ? pb : fast_sqrt(pb);
-                if (Cg) Cg[gb] = xb;
+            xa = make_float2(e.x + wo.x, e.y + wo.y);
+            xb = make_float2(e.x - wo.x, wo.y - e.y);
+        };
+        if (MODE == 0) {                                   // magnitudes only (the feature path)
+#pragma unroll 2
+            for (int k = g; k < N2 / 2; k += G) {
+                float2 xa, xb;
+                pair(k, xa, xb);
+                *reinterpret_cast<float*>(Sg + (int64_t)k * T4) = fast_sqrt(xa.x * xa.x + xa.y * xa.y);
+                *reinterpret_cast<float*>(Sg + (int64_t)(N2 - k) * T4) = fast_sqrt(xb.x * xb.x + xb.y * xb.y);
+            }
+            if (g == (N2 / 2) % G) {                       // the middle bin pairs with itself
+                float2 xa, xb;
+                pair(N2 / 2, xa, xb);
+                *reinterpret_cast<float*>(Sg + (int64_t)(N2 / 2) * T4) = fast_sqrt(xa.x * xa.x + xa.y * xa.y);
+            }
+        } else {
+            float2* Cg = cplx ? cplx + base : nullptr;
+            for (int k = g; k <= N2 / 2; k += G) {
+                const int k2 = N2 - k;
+                float2 xa, xb;
+                pair(k, xa, xb);
+                const float pa = xa.x * xa.x + xa.y * xa.y;
+                const float pb = xb.x * xb.x + xb.y * xb.y;
+                const int64_t ga = (int64_t)k * T, gb = (int64_t)k2 * T;
+                *reinterpret_cast<float*>(Sg + 4 * ga) = power ? pa : fast_sqrt(pa);
+                if (Cg) Cg[ga] = xa;
+                if (k2 != k) {
+                    *reinterpret_cast<float*>(Sg + 4 * gb) = power ? pb : fast_sqrt(pb);
+                    if (Cg) Cg[gb] = xb;
+                }
             }
         }
     }
@@ -186,7 +208,8 @@ int launch_cfg(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* p
     int rc = ensure_stft_tiles(b, tt);
     if (rc) return rc;
     if (b->n_stft_tiles == 0) return HPSS_OK;
-    auto kern = stft_fast_kernel<NFFT, HOP, NA, NB, NT>;
+    // MODE 0: magnitudes only (the feature path); MODE 1: power and / or complex output as well
+    auto kern = (power || cplx) ? stft_fast_kernel<NFFT, HOP, NA, NB, NT, 1> : stft_fast_kernel<NFFT, HOP, NA, NB, NT, 0>;
     HPSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
     kern<<<b->n_stft_tiles, NT, C::smem_bytes, st>>>(wave, b->d_sample_off, b->d_frame_off, b->d_stft_tiles,
                                                      plan->d_window, plan->d_tw_half, plan->d_tw_full, power, S,
