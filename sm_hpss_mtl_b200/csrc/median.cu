@@ -189,14 +189,21 @@ __device__ __forceinline__ void tile_fill_async(uint32_t sm_base, const float* _
                 for (int q = 0; q < NCH; ++q) fc.off[q] = reflect_idx(p0 - halo + lane + 32 * q, n0);
             }
             const float* rowp = S + __shfl_sync(0xffffffffu, li.base, 0) + (int64_t)lw * n0;
+            const uint32_t four = 4u * gridDim.y;               // = 4
             uint32_t drow = sm_base + 4u * (uint32_t)(lw * lstride + lane);
             const uint32_t dstep = 4u * (uint32_t)(kLoaderWarps * lstride);
             const int64_t sstep = (int64_t)kLoaderWarps * n0;
 #pragma unroll 2
             for (int r = lw; r < 32; r += kLoaderWarps, drow += dstep, rowp += sstep) {
 #pragma unroll
-                for (int q = 0; q < NCH; ++q)
-                    if (lane + 32 * q < span) cp_async4(drow + 128u * q, rowp + fc.off[q]);
+                for (int q = 0; q < NCH; ++q) {
+                    // byte address = row + 4 * offset as ONE IMAD.WIDE on the FMA pipe (the multiplier is a
+                    // run-time 4, so the compiler cannot turn it into the two-instruction LEA pair on the ALU
+                    // pipe, which this kernel saturates)
+                    const float* src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(rowp) +
+                                                                      (uint64_t)(uint32_t)fc.off[q] * four);
+                    if (lane + 32 * q < span) cp_async4(drow + 128u * q, src);
+                }
             }
         } else {
             for (int r = lw; r < 32; r += kLoaderWarps) {

@@ -26,6 +26,14 @@ namespace {
 
 constexpr int kWalkWarps = 4;
 
+// p + i * pitch_bytes as ONE IMAD.WIDE.U32 (FMA pipe): the ALU pipe belongs to the FMNMX stream
+__device__ __forceinline__ const float* row_ptr(const float* p, uint32_t i, uint32_t pitch_bytes) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p) + (uint64_t)i * pitch_bytes);
+}
+__device__ __forceinline__ float* row_ptr(float* p, uint32_t i, uint32_t pitch_bytes) {
+    return reinterpret_cast<float*>(reinterpret_cast<char*>(p) + (uint64_t)i * pitch_bytes);
+}
+
 struct WalkArgs {
     const float* S;
     float* perc;             // !FUSED: output (rows, T_c) per clip
@@ -63,11 +71,12 @@ median_freq_walk_kernel(WalkArgs a, const int64_t* __restrict__ frame_off, const
     }
     const int64_t in_base = (int64_t)rows * fo + (gf - fo);
     const float* col = a.S + in_base;
-    const int Ti = (int)T;                     // row pitch of this lane's clip (32-bit: one IMAD.WIDE per address)
+    const int Ti = (int)T;                     // row pitch of this lane's clip
+    const uint32_t T4 = 4u * (uint32_t)Ti;     // ... in bytes: one IMAD.WIDE.U32 per address
     // S[f] of this lane's frame, f reflected into [0, rows) (warp-uniform index)
     auto ld = [&](int f) -> float {
         const int fr = reflect_idx(f, rows);
-        return valid ? __ldg(col + (int64_t)fr * Ti) : 0.f;
+        return valid ? __ldg(row_ptr(col, (uint32_t)fr, T4)) : 0.f;
     };
 
     // ---- FUSED state (mel sweep of K3)
@@ -129,13 +138,13 @@ median_freq_walk_kernel(WalkArgs a, const int64_t* __restrict__ frame_off, const
         if (FUSED) {
 #pragma unroll
             for (int i = 0; i < (2 * G + 7) / 8; ++i) em[i] = __ldg(a.emit4 + (base >> 3) + i);
-            const float* hp = hcol + (int64_t)base * Ti;
+            const float* hp = row_ptr(hcol, (uint32_t)base, T4);
             if (interior) {
 #pragma unroll
-                for (int j = 0; j < 2 * G; ++j) hv[j] = valid ? __ldg(hp + (int64_t)j * Ti) : 0.f;
+                for (int j = 0; j < 2 * G; ++j) hv[j] = valid ? __ldg(row_ptr(hp, j, T4)) : 0.f;
             } else {
 #pragma unroll
-                for (int j = 0; j < 2 * G; ++j) hv[j] = (valid && base + j < rows) ? __ldg(hp + (int64_t)j * Ti) : 0.f;
+                for (int j = 0; j < 2 * G; ++j) hv[j] = (valid && base + j < rows) ? __ldg(row_ptr(hp, j, T4)) : 0.f;
             }
         }
         float xr[NR], o[2 * G], na[G], nb[G];
@@ -149,9 +158,9 @@ median_freq_walk_kernel(WalkArgs a, const int64_t* __restrict__ frame_off, const
         // the 2G new input rows of the next step: in flight during the stores / the mask and mel phase
         float nn[2 * G];
         if (interior) {
-            const float* np = col + (int64_t)(base + 4 * G - 1) * Ti;
+            const float* np = row_ptr(col, (uint32_t)(base + 4 * G - 1), T4);
 #pragma unroll
-            for (int i = 0; i < 2 * G; ++i) nn[i] = valid ? __ldg(np + (int64_t)i * Ti) : 0.f;
+            for (int i = 0; i < 2 * G; ++i) nn[i] = valid ? __ldg(row_ptr(np, i, T4)) : 0.f;
         } else if (s + 1 < nsteps) {
 #pragma unroll
             for (int i = 0; i < 2 * G; ++i) nn[i] = ld(base + 4 * G - 1 + i);
@@ -159,14 +168,14 @@ median_freq_walk_kernel(WalkArgs a, const int64_t* __restrict__ frame_off, const
 
         if (!FUSED) {
             if (valid) {
-                float* dst = pcol + (int64_t)base * Ti;
+                float* dst = row_ptr(pcol, (uint32_t)base, T4);
                 if (interior) {
 #pragma unroll
-                    for (int j = 0; j < 2 * G; ++j) dst[(int64_t)j * Ti] = o[j];
+                    for (int j = 0; j < 2 * G; ++j) *row_ptr(dst, j, T4) = o[j];
                 } else {
 #pragma unroll
                     for (int j = 0; j < 2 * G; ++j)
-                        if (base + j < rows) dst[(int64_t)j * Ti] = o[j];
+                        if (base + j < rows) *row_ptr(dst, j, T4) = o[j];
                 }
             }
         } else {
@@ -258,9 +267,10 @@ median_freq_walk_group_kernel(const float* __restrict__ S, float* __restrict__ p
     const int64_t in_base = (int64_t)rows * fo + (gf - fo);
     const float* col = S + in_base;
     float* pcol = perc + in_base;
+    const uint32_t T4 = 4u * (uint32_t)Ti;
     auto ld = [&](int f) -> float {
         const int fr = reflect_idx(f, rows);
-        return valid ? __ldg(col + (int64_t)fr * Ti) : 0.f;
+        return valid ? __ldg(row_ptr(col, (uint32_t)fr, T4)) : 0.f;
     };
     float x[NX];
 #pragma unroll
@@ -273,9 +283,9 @@ median_freq_walk_group_kernel(const float* __restrict__ S, float* __restrict__ p
         const bool interior = fnew + G - 1 < rows;          // warp-uniform: no reflection in the next loads
         float nn[G];
         if (interior) {
-            const float* np = col + (int64_t)fnew * Ti;
+            const float* np = row_ptr(col, (uint32_t)fnew, T4);
 #pragma unroll
-            for (int j = 0; j < G; ++j) nn[j] = valid ? __ldg(np + (int64_t)j * Ti) : 0.f;
+            for (int j = 0; j < G; ++j) nn[j] = valid ? __ldg(row_ptr(np, j, T4)) : 0.f;
         } else if (g + 1 < ngroups) {
 #pragma unroll
             for (int j = 0; j < G; ++j) nn[j] = ld(fnew + j);
@@ -283,10 +293,10 @@ median_freq_walk_group_kernel(const float* __restrict__ S, float* __restrict__ p
         float o[G];
         MedianGroup<K>::run(x, o);
         if (valid) {
-            float* dst = pcol + (int64_t)base * Ti;
+            float* dst = row_ptr(pcol, (uint32_t)base, T4);
 #pragma unroll
             for (int j = 0; j < G; ++j)
-                if (base + j < rows) dst[(int64_t)j * Ti] = o[j];
+                if (base + j < rows) *row_ptr(dst, j, T4) = o[j];
         }
 #pragma unroll
         for (int i = 0; i < K - 1; ++i) x[i] = x[i + G];
