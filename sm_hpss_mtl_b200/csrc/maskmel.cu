@@ -316,6 +316,10 @@ mask_mel_sweep2_kernel(const float* __restrict__ S, const float* __restrict__ ha
         ++cur;
     };
     const int rows_u = (rows + U - 1) / U * U;         // the tables are zero padded to a multiple of 64 rows
+    const uint32_t T4 = 4u * (uint32_t)T;              // row pitch in bytes: one IMAD.WIDE.U32 per address (FMA pipe)
+    auto rowp = [&](const float* p, uint32_t f) {
+        return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p) + (uint64_t)f * T4);
+    };
 #pragma unroll 1
     for (int f0 = 0; f0 < rows_u; f0 += U) {
         float sv[U], hv[U], pv[U];
@@ -325,13 +329,12 @@ mask_mel_sweep2_kernel(const float* __restrict__ S, const float* __restrict__ ha
         for (int u = 0; u < U; ++u) {
             sv[u] = 0.f; hv[u] = 0.f; pv[u] = 0.f;
             if (fl.valid && f0 + u < rows) {
-                sv[u] = __ldg(sp + (int64_t)u * T);
-                hv[u] = __ldg(hp + (int64_t)u * T);
-                pv[u] = __ldg(pp + (int64_t)u * T);
+                sv[u] = __ldg(rowp(sp, f0 + u));
+                hv[u] = __ldg(rowp(hp, f0 + u));
+                pv[u] = __ldg(rowp(pp, f0 + u));
             }
             w[u] = __ldg(sweep_w + f0 + u);
         }
-        sp += (int64_t)U * T; hp += (int64_t)U * T; pp += (int64_t)U * T;
         float H[U], P[U];
         softmask_batch<U>(sv, hv, pv, H, P);
 #pragma unroll

@@ -99,11 +99,13 @@ __device__ __forceinline__ void tile_store(const float* __restrict__ sm, float* 
             if (n0 == 0 || p0 >= n0) return;
             float* row0 = out + __shfl_sync(0xffffffffu, li.base, 0) + p0;
             const int lim = min(TT, n0 - p0);
+            const uint32_t pitch = 4u * (uint32_t)n0;      // bytes between rows: one IMAD.WIDE.U32 per address (FMA pipe)
             for (int pos = lane; pos < lim; pos += 32) {
                 const float* s = sm + pos;
-                float* d = row0 + pos;
+                char* d0 = reinterpret_cast<char*>(row0 + pos);
 #pragma unroll 8
-                for (int r = 0; r < 32; ++r, s += lstride, d += n0) *d = *s;
+                for (int r = 0; r < 32; ++r, s += lstride)
+                    *reinterpret_cast<float*>(d0 + (uint64_t)(uint32_t)r * pitch) = *s;
             }
             return;
         }
