@@ -377,3 +377,31 @@ def test_perc_mask_mel_fused_equals_separate_kernels(ctx, k, n_fft, n_mels, Ts):
         assert torch.equal(got, want)
         if log_power:
             assert torch.equal(cm_g, cm_w)
+
+
+def test_no_out_of_bounds_writes_canary(ctx):
+    """compute-sanitizer is closed on the GPU pool, so out-of-bounds writes are looked for by hand: the feature
+    and moment buffers sit between canary regions that must stay untouched (ragged batch, odd clip lengths,
+    both median kernel families, clip + moments fused)."""
+    Ls = [16000, 4001, 23457, 1601, 400]
+    cls = [0, 1, 2, 0, 1]
+    wave = to_dev(np.concatenate([synth.synth_clip(300 + i, L) for i, L in enumerate(Ls)]))
+    for (lh, lp) in [(31, 31), (21, 11), (15, 64)]:
+        prm = engine.make_params(l_harm=lh, l_perc=lp, n_mels=40)
+        batch = engine.Batch(ctx, clip_lengths=Ls, n_fft=400, hop_length=160)
+        D = engine.feature_rows(prm)
+        n = D * batch.total_frames
+        pad = 4096
+        big = torch.full((n + 2 * pad,), float("nan"), dtype=torch.float32, device="cuda")
+        n_acc = 3 * D + D + 3 + 1
+        big_acc = torch.full((n_acc + 64,), -7.0, dtype=torch.float64, device="cuda")
+        acc = big_acc[32:32 + n_acc]
+        acc.zero_()
+        out = big[pad:pad + n]
+        engine.featuregram_moments(batch, wave, prm, cls, 3, out=out, acc=acc)
+        torch.cuda.synchronize()
+        assert torch.isfinite(out).all()
+        assert torch.isnan(big[:pad]).all() and torch.isnan(big[pad + n:]).all()
+        assert (big_acc[:32] == -7.0).all() and (big_acc[32 + n_acc:] == -7.0).all()
+        ref = engine.featuregram(batch, wave, prm)
+        assert torch.equal(ref, out)
