@@ -251,6 +251,12 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
                    int64_t n_items, int NB) {
     constexpr int G = MedianGroup<K>::G;
     constexpr int HALO = K / 2;
+    // stateful double steps where K has them (time axis; the frequency axis has its own walk kernel).  MIXED:
+    // same G as the stateless group, which then finishes tiles with an odd number of groups; otherwise tiles
+    // are whole steps (launch_fast rounds TT to kGranule<K, TIME_AXIS>)
+    constexpr bool STEP = TIME_AXIS && MedianStep<K>::available;
+    constexpr int GS = MedianStep<K>::G;
+    constexpr bool MIXED = STEP && GS == G;
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int span = TT + K - 1;
@@ -300,42 +306,37 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
             if (live) {
                 const int ng = min(NG, (li.n - p0 + G - 1) / G);
                 int g = 0;
-                if constexpr (MedianStep<K>::available) {
+                if constexpr (STEP) {
                     // stateful walk: two groups per step, the sorted blocks C2, C3 of one step are C0, C1 of the next
-                    static_assert(MedianStep<K>::G == G, "step and group networks must agree on G");
                     constexpr int NR = MedianStep<K>::NRAW;
-                    if (ng >= 2) {
-                        float ca[G], cb[G];
+                    const int live = min(TT, li.n - p0);                       // outputs this line needs
+                    const int nst = MIXED ? ng / 2 : (live + 2 * GS - 1) / (2 * GS);
+                    if (nst > 0) {
+                        float ca[GS], cb[GS];
                         {
-                            float r0[G], r1[G];
+                            float r0[GS], r1[GS];
 #pragma unroll
-                            for (int i = 0; i < G; ++i) {
-                                r0[i] = sm[sidx<TIME_AXIS>(lane, G - 1 + i, lstride)];
-                                r1[i] = sm[sidx<TIME_AXIS>(lane, 2 * G - 1 + i, lstride)];
+                            for (int i = 0; i < GS; ++i) {
+                                r0[i] = sm[sidx<TIME_AXIS>(lane, GS - 1 + i, lstride)];
+                                r1[i] = sm[sidx<TIME_AXIS>(lane, 2 * GS - 1 + i, lstride)];
                             }
                             MedianStep<K>::sort(r0, ca);
                             MedianStep<K>::sort(r1, cb);
                         }
-                        for (; g + 2 <= ng; g += 2) {
-                            float xr[NR], o[2 * G], na[G], nb[G];
+                        for (int st = 0; st < nst; ++st) {
+                            const int b0 = 2 * GS * st;
+                            float xr[NR], o[2 * GS], na[GS], nb[GS];
 #pragma unroll
                             for (int i = 0; i < NR; ++i)
-                                xr[i] = sm[sidx<TIME_AXIS>(lane, g * G + MedianStep<K>::raw_pos(i), lstride)];
+                                xr[i] = sm[sidx<TIME_AXIS>(lane, b0 + MedianStep<K>::raw_pos(i), lstride)];
                             MedianStep<K>::run(ca, cb, xr, o, na, nb);
 #pragma unroll
-                            for (int i = 0; i < G; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
-                            if (TIME_AXIS) {
+                            for (int i = 0; i < GS; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
 #pragma unroll
-                                for (int j = 0; j < 2 * G; ++j) sm[sidx<TIME_AXIS>(lane, g * G + j, lstride)] = o[j];
-                            } else {
-                                float* dst = out + li.base + (int64_t)(p0 + g * G) * li.estride;
-                                const int nj = min(2 * G, li.n - p0 - g * G);
-#pragma unroll
-                                for (int j = 0; j < 2 * G; ++j)
-                                    if (j < nj) dst[(int64_t)j * li.estride] = o[j];
-                            }
+                            for (int j = 0; j < 2 * GS; ++j) sm[sidx<TIME_AXIS>(lane, b0 + j, lstride)] = o[j];
                         }
                     }
+                    g = MIXED ? 2 * nst : ng;                                 // !MIXED: the steps covered the tile
                 }
                 for (; g < ng; ++g) {
                     float x[K + G - 1], o[G];
@@ -644,13 +645,16 @@ median_generic_kernel(const float* __restrict__ S, float* __restrict__ out, cons
 template <int K, bool TIME_AXIS>
 int launch_fast(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_frame_off, const int32_t* d_block_clip, int rows,
                 int64_t n_lines, int64_t max_len, cudaStream_t st) {
-    constexpr int G = MedianGroup<K>::G;
+    // tile length granule: a stateless group, or a whole stateful double step when its G differs from the group's
+    constexpr int G = (TIME_AXIS && MedianStep<K>::available && MedianStep<K>::G != MedianGroup<K>::G)
+                          ? 2 * MedianStep<K>::G : MedianGroup<K>::G;
     // largest tile (multiple of G outputs, at most 16 groups) that still leaves room for a ring of
     // kComputeWarps + 2 buffers in the opt-in shared memory
     const size_t per_buf = ((size_t)ctx->max_smem_optin - 512) / (kComputeWarps + 2) - 16;
     const int max_span = (int)(per_buf / (32 * sizeof(float))) - 1;
     int tt_max = (max_span - (K - 1)) / G * G;
-    if (tt_max > 16 * G) tt_max = 16 * G;
+    const int tt_cap = std::max(16 * G, 128 / G * G);      // small kernels have small groups: still ~128 outputs per tile
+    if (tt_max > tt_cap) tt_max = tt_cap;
     if (tt_max < G) {
         set_error("median k=%d does not fit the shared-memory tile ring", K);
         return HPSS_ERR_UNSUPPORTED;

@@ -48,14 +48,14 @@ struct WalkArgs {
 };
 
 template <int K, bool FUSED, int LOGP>
-__global__ void __launch_bounds__(kWalkWarps * 32, FUSED ? 3 : 4)
+__global__ void __launch_bounds__(kWalkWarps * 32, (FUSED || K > 35) ? (K > 47 ? 2 : 3) : 4)
 median_freq_walk_kernel(WalkArgs a, const int64_t* __restrict__ frame_off, const int32_t* __restrict__ block_clip,
                         int64_t total_frames, int rows) {
     using Step = MedianStep<K>;
     constexpr int G = Step::G;
     constexpr int HALO = K / 2;               // = 2G - 1
     constexpr int NR = Step::NRAW;            // = 6G - 11 ... raw inputs of a step, in step_raw_index order
-    static_assert((2 * G) % 8 == 0, "a step covers whole words of the emission table");
+    static_assert(!FUSED || (2 * G) % 8 == 0, "a fused step covers whole words of the emission table");
     static_assert(K == 4 * G - 1 && NR == 2 * (G - 1) + 2 * G + (G - 1), "stateful step layout");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t g0 = ((int64_t)blockIdx.x * kWalkWarps + warp) * 32;
@@ -327,29 +327,23 @@ int launch_median_freq_walk(hpss_ctx* ctx, const hpss_batch* b, const float* S, 
     const int64_t total = b->frame_off[b->n_clips];
     WalkArgs wa{};
     wa.S = S; wa.perc = out;
-#define HPSS_WALK_K(KK)                                                              \
-    if (k == KK) {                                                                   \
-        if constexpr (MedianStep<KK>::available) {                                   \
-            *handled = true;                                                         \
-            if (total == 0) return HPSS_OK;                                          \
-            return launch_walk<KK, false>(b, wa, rows, total, st);                   \
-        }                                                                            \
-    }
-    HPSS_WALK_K(15) HPSS_WALK_K(31)
-#undef HPSS_WALK_K
-#define HPSS_WALK_GROUP_K(KK)                                                                                       \
+#define HPSS_WALK_ANY_K(KK)                                                                                         \
     if (k == KK) {                                                                                                  \
         *handled = true;                                                                                            \
         if (total == 0) return HPSS_OK;                                                                             \
-        const int64_t n_warps = (total + 31) / 32;                                                                  \
-        const unsigned grid = (unsigned)((n_warps + kWalkWarps - 1) / kWalkWarps);                                  \
-        median_freq_walk_group_kernel<KK><<<grid, kWalkWarps * 32, 0, st>>>(S, out, b->d_frame_off, b->d_block_clip, \
-                                                                            total, rows);                           \
-        HPSS_LAUNCHED("median_freq_walk_group_kernel");                                                             \
-        return HPSS_OK;                                                                                             \
+        if constexpr (MedianStep<KK>::available) {                                                                  \
+            return launch_walk<KK, false>(b, wa, rows, total, st);                                                  \
+        } else {                                                                                                    \
+            const int64_t n_warps = (total + 31) / 32;                                                              \
+            const unsigned grid = (unsigned)((n_warps + kWalkWarps - 1) / kWalkWarps);                              \
+            median_freq_walk_group_kernel<KK><<<grid, kWalkWarps * 32, 0, st>>>(S, out, b->d_frame_off,             \
+                                                                                b->d_block_clip, total, rows);      \
+            HPSS_LAUNCHED("median_freq_walk_group_kernel");                                                         \
+            return HPSS_OK;                                                                                         \
+        }                                                                                                           \
     }
-    HPSS_MEDIAN_FAST_KS(HPSS_WALK_GROUP_K)
-#undef HPSS_WALK_GROUP_K
+    HPSS_MEDIAN_FAST_KS(HPSS_WALK_ANY_K)
+#undef HPSS_WALK_ANY_K
     return HPSS_OK;
 }
 

@@ -25,6 +25,7 @@ Usage:  python tools/gen_median_networks.py [--out PATH] [--ks 3,5,...]
 from __future__ import annotations
 
 import argparse
+import os
 import sys
 from dataclasses import dataclass, field
 
@@ -214,51 +215,112 @@ def merge_lists(P: Prog, A, B, cache):
 
 
 def shared_extras(P: Prog, X, G, cache):
-    """sorted X[j+1 .. j+G-2] for j = 0, 2, .., G-2, built from nested suffix sorts of the left extras
-    X[:G-1] and nested prefix sorts of the right extras X[G-1:] (each pair of values is sorted once)."""
+    """sorted X[j+1 .. j+G-2] for the output pairs j = 0, 2, .. (and, for odd G, sorted X[G-1 .. 2G-3] for the
+    last, unpaired output under key G-1), built from nested suffix sorts of the left extras X[:G-1] and nested
+    prefix sorts of the right extras X[G-1:] (values are added two at a time, each pair is sorted once)."""
     L, R = X[:G - 1], X[G - 1:]
-    suf, pre = {0: []}, {0: []}
-    for k in range(2, G - 1, 2):
-        suf[k] = merge_lists(P, sort_wires(P, [L[G - 1 - k], L[G - k]]), suf[k - 2], cache)
-        pre[k] = merge_lists(P, pre[k - 2], sort_wires(P, [R[k - 2], R[k - 1]]), cache)
-    return {j: merge_lists(P, suf[G - 2 - j], pre[j], cache) for j in range(0, G, 2)}
+    suf_memo, pre_memo = {0: []}, {0: []}
+
+    def suf(k):                                   # sorted last k values of L
+        if k not in suf_memo:
+            step = 2 if k >= 2 else 1
+            head = sort_wires(P, L[G - 1 - k:G - 1 - k + step])
+            suf_memo[k] = merge_lists(P, head, suf(k - step), cache)
+        return suf_memo[k]
+
+    def pre(k):                                   # sorted first k values of R
+        if k not in pre_memo:
+            step = 2 if k >= 2 else 1
+            tail = sort_wires(P, R[k - step:k])
+            pre_memo[k] = merge_lists(P, pre(k - step), tail, cache)
+        return pre_memo[k]
+
+    out = {}
+    for j in range(0, G - 1, 2):
+        out[j] = merge_lists(P, suf(G - 2 - j), pre(j), cache)
+    if G % 2 == 1:
+        out[G - 1] = pre(G - 1)
+    return out
+
+
+def step_layout(K, G):
+    """Positions (relative to the first input of the double step) used by gen_step.
+    K = 4G - 1 + 2E: the core of a group is the block-aligned middle 3G of the K - G + 1 values common to its G
+    windows, E more values on each side are treated as extras."""
+    assert (K - (4 * G - 1)) % 2 == 0 and K >= 4 * G - 1
+    E = (K - (4 * G - 1)) // 2
+    c0 = G - 1 + E                                  # first position of block C0
+    blocks = [list(range(c0 + b * G, c0 + (b + 1) * G)) for b in range(4)]
+    extras = []
+    for base in (0, G):                             # the two groups of the step
+        left = list(range(base, base + G - 1 + E))                       # x[base .. base+G-2+E]
+        right = list(range(base + 4 * G - 1 + E, base + K + G - 1))      # x[base+4G-1+E .. base+K+G-2]
+        extras.append((left, right))
+    raw = sorted(set(extras[0][0] + extras[0][1] + extras[1][0] + extras[1][1] + blocks[2] + blocks[3]))
+    return E, c0, blocks, extras, raw
 
 
 def step_raw_index(K, G):
     """window-relative input positions a stateful step reads raw (see gen_step)"""
-    return list(range(0, G - 1)) + list(range(G, 2 * G - 1)) + list(range(3 * G - 1, K + 2 * G - 1))
+    return step_layout(K, G)[4]
 
 
 def gen_step(K, G):
-    """Stateful double step for K = 4G - 1: 2G consecutive outputs per call, walking along a line.
+    """Stateful double step, K = 4G - 1 + 2E: 2G consecutive outputs per call, walking along a line.
 
-    With x[i] the inputs of the 2G windows (x[j .. j+K-1] for output j), the blocks
-    C0 = x[G-1..2G-2], C1 = x[2G-1..3G-2], C2 = x[3G-1..4G-2], C3 = x[4G-1..5G-2] tile the two cores
-    (outputs 0..G-1: C0 u C1 u C2, outputs G..2G-1: C1 u C2 u C3).  C0 and C1 arrive SORTED from the previous
-    step (its C2, C3); C2, C3 are sorted here and handed on; C1 u C2 is merged once and serves both cores.
+    With x[i] the inputs of the 2G windows (x[j .. j+K-1] for output j), the blocks C0..C3 (G values each,
+    starting at x[G-1+E]) tile the two cores (outputs 0..G-1: C0 u C1 u C2, outputs G..2G-1: C1 u C2 u C3).
+    C0 and C1 arrive SORTED from the previous step (its C2, C3); C2, C3 are sorted here and handed on; C1 u C2
+    is merged once and serves both cores.  The G-1+2E values of a window outside its core are its extras:
+    neighbouring windows share all but one of them, and nested suffix / prefix sorts are shared by the pairs.
     Program inputs: ca[G], cb[G] (sorted), then the raw values x[i], i in step_raw_index(K, G).
     Program outputs: o[2G], then sorted C2[G], C3[G]."""
-    assert K == 4 * G - 1 and G % 2 == 0
+    E, c0, blocks, extras, raw_idx = step_layout(K, G)
     h = K // 2
-    raw_idx = step_raw_index(K, G)
     P = Prog(2 * G + len(raw_idx))
     ca, cb = list(range(0, G)), list(range(G, 2 * G))
     xw = {i: 2 * G + n for n, i in enumerate(raw_idx)}
     cache = {}
-    cc = sort_wires(P, [xw[i] for i in range(3 * G - 1, 4 * G - 1)])
-    cd = sort_wires(P, [xw[i] for i in range(4 * G - 1, 5 * G - 1)])
+    cc = sort_wires(P, [xw[i] for i in blocks[2]])
+    cd = sort_wires(P, [xw[i] for i in blocks[3]])
     pair = merge_lists(P, cb, cc, cache)
     outs = []
-    for (core, base) in ((merge_lists(P, ca, pair, cache), 0), (merge_lists(P, pair, cd, cache), G)):
-        m = core[h - G + 1:h + 1]
-        X = [xw[base + i] for i in range(0, G - 1)] + [xw[base + K + i] for i in range(0, G - 1)]
-        sh = shared_extras(P, X, G, cache)
+    for gi, core in enumerate((merge_lists(P, ca, pair, cache), merge_lists(P, pair, cd, cache))):
+        left, right = extras[gi]
+        nx = G - 1 + 2 * E                          # extras per window
+        # answer = rank h of core (3G sorted) u extras (nx): candidates from the core are its ranks h-nx .. h
+        m = core[h - nx:h + 1]
+        Lw = [xw[i] for i in left]
+        Rw = [xw[i] for i in right]
+        # window j (j = 0..G-1) owns left[j:] and right[:E+j]
+        suf_memo, pre_memo = {0: []}, {0: []}
+
+        def suf(k):                                 # sorted last k values of the left extras
+            if k not in suf_memo:
+                step = 2 if k >= 2 else 1
+                head = sort_wires(P, Lw[len(Lw) - k:len(Lw) - k + step])
+                suf_memo[k] = merge_lists(P, head, suf(k - step), cache)
+            return suf_memo[k]
+
+        def pre(k):                                 # sorted first k values of the right extras
+            if k not in pre_memo:
+                step = 2 if k >= 2 else 1
+                tail = sort_wires(P, Rw[k - step:k])
+                pre_memo[k] = merge_lists(P, pre(k - step), tail, cache)
+            return pre_memo[k]
+
         o = [None] * G
-        for j in range(0, G, 2):
-            u = merge_select(P, m, sh[j], G - 2)
-            w = merge_select(P, m, sh[j], G - 1)
-            o[j] = P.mx(u, P.mn(X[j], w))
-            o[j + 1] = P.mx(u, P.mn(X[j + G - 1], w))
+        for j in range(0, G - 1, 2):
+            # windows j and j+1 share left[j+1:] and right[:E+j]; private: left[j] (window j), right[E+j] (window j+1)
+            sh = merge_lists(P, suf(len(Lw) - j - 1), pre(E + j), cache)      # nx - 1 values
+            u = merge_select(P, m, sh, nx - 1)
+            w = merge_select(P, m, sh, nx)
+            o[j] = P.mx(u, P.mn(Lw[j], w))
+            o[j + 1] = P.mx(u, P.mn(Rw[E + j], w))
+        if G % 2 == 1:                              # last output of an odd group
+            j = G - 1
+            e = merge_lists(P, suf(len(Lw) - j), pre(E + j), cache)           # all nx extras
+            o[j] = merge_select(P, m, e, nx)
         outs += o
     P.outs = outs + cc + cd
     return P.dce()
@@ -266,13 +328,13 @@ def gen_step(K, G):
 
 def verify_step(P: Prog, K, G, trials=600, steps=4, seed=0):
     rng = np.random.default_rng(seed + 977 * K)
-    raw_idx = step_raw_index(K, G)
+    E, c0, blocks, extras, raw_idx = step_layout(K, G)
     L = K - 1 + 2 * G * steps
     for data in (rng.standard_normal((L, trials)).astype(np.float32),
                  rng.integers(0, 3, size=(L, trials)).astype(np.float32),
                  np.sort(rng.standard_normal((L, trials)).astype(np.float32), axis=0)):
-        ca = np.sort(data[G - 1:2 * G - 1], axis=0)
-        cb = np.sort(data[2 * G - 1:3 * G - 1], axis=0)
+        ca = np.sort(data[blocks[0]], axis=0)
+        cb = np.sort(data[blocks[1]], axis=0)
         for st in range(steps):
             base = 2 * G * st
             x = data[base:base + K + 2 * G - 1]
@@ -442,8 +504,8 @@ def main():
         chunks.append("")
         table.append((K, G))
     # stateful double steps (K = 4G - 1) and the block sorts that start a line
-    # (only where the stateless group of the same K has the same G: the kernel finishes odd tiles with it)
-    step_ks = [(K, (K + 1) // 4) for K, G in table if K in (15, 31, 63) and G == (K + 1) // 4]
+    step_maxk = int(os.environ.get('HPSS_STEP_MAXK', '55'))     # measured: beyond 55 the stateless group is faster (registers)
+    step_ks = [(K, (K + 1) // 4) for K, G in table if (K + 1) % 4 == 0 and 7 <= K <= step_maxk]
     sorts_done = set()
     for K, G in step_ks:
         P = gen_step(K, G)
