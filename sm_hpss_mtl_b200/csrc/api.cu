@@ -266,6 +266,9 @@ static int make_batch(hpss_ctx* ctx, const std::vector<int64_t>& samples, const 
         b->frame_off[c + 1] = b->frame_off[c] + frames[c];
         b->max_frames = std::max(b->max_frames, frames[c]);
     }
+    b->uniform_frames = (n > 0) ? frames[0] : 0;
+    for (int c = 1; c < n; ++c)
+        if (frames[c] != frames[0]) { b->uniform_frames = 0; break; }
     // clip of the first frame of every 32-frame block (empty clips are skipped)
     const int64_t total = b->frame_off[n];
     std::vector<int32_t> block_clip((size_t)((total + 31) / 32) + 1, 0);

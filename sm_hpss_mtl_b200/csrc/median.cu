@@ -36,10 +36,16 @@ struct LineInfo {
 template <bool TIME_AXIS>
 __device__ __forceinline__ LineInfo lane_line(const int64_t* __restrict__ frame_off,
                                               const int32_t* __restrict__ block_clip, int rows, int64_t n_lines,
-                                              int64_t line) {
+                                              int64_t line, int uniform_T = 0) {
     LineInfo li;
     li.base = 0; li.n = 0; li.estride = 1;
     if (line >= n_lines) return li;
+    if (TIME_AXIS && uniform_T > 0) {
+        // every clip has uniform_T frames: line (c, f) starts at (c * rows + f) * T = line * T -- no table lookups
+        li.base = line * uniform_T;
+        li.n = uniform_T;
+        return li;
+    }
     if (TIME_AXIS) {
         const int c = (int)(line / rows);
         const int f = (int)(line - (int64_t)c * rows);
@@ -248,7 +254,7 @@ template <int K, bool TIME_AXIS>
 __global__ void __launch_bounds__(kRingThreads, 1)
 median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const int64_t* __restrict__ frame_off,
                    const int32_t* __restrict__ block_clip, int rows, int64_t n_lines, int TT, int n_ptiles,
-                   int64_t n_items, int NB) {
+                   int64_t n_items, int NB, int uniform_T) {
     constexpr int G = MedianGroup<K>::G;
     constexpr int HALO = K / 2;
     // stateful double steps where K has them (time axis; the frequency axis has its own walk kernel).  MIXED:
@@ -286,7 +292,7 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
             const int64_t item = blockIdx.x + n * gridDim.x;
             const int64_t lb = item / n_ptiles;
             const int p0 = (int)(item - lb * n_ptiles) * TT;
-            const LineInfo li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane);
+            const LineInfo li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane, uniform_T);
             if (use > 0) mbar_wait(empty0 + 8u * b, (use - 1) & 1u);
             tile_fill_async<TIME_AXIS>(smem_u32(smem + (size_t)b * tile_floats), S, li, lane, lw, p0, HALO, span, lstride, fc);
             cp_async_arrive(full0 + 8u * b);
@@ -300,7 +306,7 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
             const int64_t item = blockIdx.x + n * gridDim.x;
             const int64_t lb = item / n_ptiles;
             const int p0 = (int)(item - lb * n_ptiles) * TT;
-            const LineInfo li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane);
+            const LineInfo li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane, uniform_T);
             const bool live = li.n > 0 && p0 < li.n;
             mbar_wait(full0 + 8u * b, use & 1u);
             if (live) {
@@ -644,7 +650,7 @@ median_generic_kernel(const float* __restrict__ S, float* __restrict__ out, cons
 
 template <int K, bool TIME_AXIS>
 int launch_fast(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_frame_off, const int32_t* d_block_clip, int rows,
-                int64_t n_lines, int64_t max_len, cudaStream_t st) {
+                int64_t n_lines, int64_t max_len, int uniform_T, cudaStream_t st) {
     // tile length granule: a stateless group, or a whole stateful double step when its G differs from the group's
     constexpr int G = (TIME_AXIS && MedianStep<K>::available && MedianStep<K>::G != MedianGroup<K>::G)
                           ? 2 * MedianStep<K>::G : MedianGroup<K>::G;
@@ -675,7 +681,7 @@ int launch_fast(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_fram
     int64_t grid = (n_items + kComputeWarps - 1) / kComputeWarps;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
     kern<<<(unsigned)grid, kRingThreads, smem, st>>>(S, out, d_frame_off, d_block_clip, rows, n_lines, TT, n_ptiles,
-                                                     n_items, NB);
+                                                     n_items, NB, uniform_T);
     HPSS_LAUNCHED("median_fast_kernel");
     return HPSS_OK;
 }
@@ -789,6 +795,7 @@ int launch_median(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, 
     if (total_frames == 0) return HPSS_OK;
     const int64_t n_lines = time_axis ? (int64_t)b->n_clips * rows : total_frames;
     const int64_t max_len = time_axis ? b->max_frames : rows;
+    const int uniform_T = (b->uniform_frames > 0 && b->uniform_frames < 0x7fffffff) ? (int)b->uniform_frames : 0;
     if (k == 1) {
         HPSS_CUDA(cudaMemcpyAsync(out, S, sizeof(float) * (size_t)rows * total_frames, cudaMemcpyDeviceToDevice, st));
         return HPSS_OK;
@@ -804,9 +811,9 @@ int launch_median(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, 
 #define HPSS_DISPATCH_K(KK)                                                                                   \
     if (k == KK) {                                                                                            \
         return time_axis ? launch_fast<KK, true>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines,      \
-                                                 max_len, st)                                                 \
+                                                 max_len, uniform_T, st)                                      \
                          : launch_fast<KK, false>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines,     \
-                                                  max_len, st);                                               \
+                                                  max_len, 0, st);                                            \
     }
     HPSS_MEDIAN_FAST_KS(HPSS_DISPATCH_K)
 #undef HPSS_DISPATCH_K
