@@ -4,6 +4,10 @@
 //
 // Reference: lib/preprocessing.py:461-586 (two-pass corpus statistics), :590-614 and
 // tools.pyx:138-166 (scale_data), :137-292 + tools.pyx:21-38 (patches).
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace hpss {
@@ -168,6 +172,106 @@ moments_kernel(float* __restrict__ feat, const int64_t* __restrict__ frame_off,
     }
 }
 
+// The same moments for a batch of equal, short clips (every clip T <= 128 frames: the training-segment shape of
+// BASELINE.json configs[1]).  Row d of clip c is the T contiguous floats at ((c * D) + d) * T, so a warp that owns
+// row d walks the clips with a constant pointer stride and lane predicates that never change; per clip it needs
+// the class and (CLIP) one threshold, nothing else.  Four clips (sixteen loads) are in flight per warp.  The
+// per-class float64 sums live in shared memory ([class][lane], one private slot per lane: no atomics), the sum
+// of squares in a register.
+template <int MAXC, bool CLIP>
+__global__ void __launch_bounds__(kThreads)
+moments_uniform_kernel(float* __restrict__ feat, int n_clips, int T, int clips_per_chunk, int D,
+                       const int32_t* __restrict__ clip_class, int n_classes, double* __restrict__ g_sum,
+                       double* __restrict__ g_sumsq, double* __restrict__ g_count, double* __restrict__ g_nonfinite,
+                       const uint32_t* __restrict__ clip_max, int rows_per_stream, int n_streams, float top_db) {
+    __shared__ double s_cls[kWarps][MAXC][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.y * kWarps + warp;
+    constexpr int NC = 4;                                    // clips in flight
+    if (d < D) {
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) s_cls[warp][k][lane] = 0.0;
+        double q = 0.0;
+        unsigned bad = 0;
+        const int stream = CLIP ? d / rows_per_stream : 0;
+        const int c0 = blockIdx.x * clips_per_chunk;
+        const int c1 = min(n_clips, c0 + clips_per_chunk);
+        const size_t pitch = (size_t)D * T;                  // floats between the same row of consecutive clips
+        float* row = feat + (size_t)c0 * pitch + (size_t)d * T;
+        bool in[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) in[u] = lane + 32 * u < T;
+        for (int c = c0; c < c1; c += NC) {
+            float x[NC][4];
+            int cls[NC];
+            float thr[NC];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const bool live = c + i < c1;
+                cls[i] = live ? __ldg(clip_class + c + i) : -1;
+                thr[i] = -INFINITY;
+                if (CLIP && live) thr[i] = ordered_to_float(__ldg(clip_max + (size_t)n_streams * (c + i) + stream)) - top_db;
+                float* r = row + (size_t)i * pitch;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    x[i][u] = 0.f;
+                    if (live && in[u]) x[i][u] = CLIP ? r[lane + 32 * u] : __ldg(r + lane + 32 * u);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                if (cls[i] < 0) continue;                    // warp-uniform
+                float* r = row + (size_t)i * pitch;
+                float ps = 0.f, pq = 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (CLIP) {
+                        if (in[u] && x[i][u] < thr[i]) { x[i][u] = thr[i]; r[lane + 32 * u] = thr[i]; }
+                    }
+                    ps += x[i][u];
+                    pq = fmaf(x[i][u], x[i][u], pq);
+                }
+                if (!isfinite(pq)) {                         // rare: redo this lane's values one by one
+                    ps = 0.f; pq = 0.f;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float v = x[i][u];
+                        if (!isfinite(v)) { v = 0.f; ++bad; }
+                        if (fabsf(v) > 1e18f) {              // the square would overflow float32
+                            q = fma((double)v, (double)v, q);
+                            s_cls[warp][cls[i]][lane] += (double)v;
+                            v = 0.f;
+                        }
+                        ps += v;
+                        pq = fmaf(v, v, pq);
+                    }
+                }
+                q += (double)pq;
+                s_cls[warp][cls[i]][lane] += (double)ps;
+            }
+            row += (size_t)NC * pitch;
+        }
+        q = warp_sum(q);
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) {
+            if (k < n_classes) {
+                const double t = warp_sum(s_cls[warp][k][lane]);
+                if (lane == 0 && t != 0.0) atomicAdd(g_sum + (size_t)k * D + d, t);
+            }
+        }
+        bad = __reduce_add_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            if (q != 0.0) atomicAdd(g_sumsq + d, q);
+            if (bad) atomicAdd(g_nonfinite, (double)bad);
+        }
+    }
+    // frame counts per class (clip granularity), once
+    if (blockIdx.y == 0) {
+        for (int c = blockIdx.x * kThreads + threadIdx.x; c < n_clips; c += gridDim.x * kThreads)
+            atomicAdd(g_count + clip_class[c], (double)T);
+    }
+}
+
 // (x - mean) / (stdev + eps) in float64, lane = frame
 __global__ void __launch_bounds__(kThreads)
 scale_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_off,
@@ -248,6 +352,27 @@ static int launch_moments_impl(hpss_ctx* ctx, const hpss_batch* b, float* feat, 
     if (n_classes > 8) {
         set_error("moments: at most 8 classes are supported (got %d)", n_classes);
         return HPSS_ERR_UNSUPPORTED;
+    }
+    if (b->uniform_frames > 0 && b->uniform_frames <= 128 && !getenv("HPSS_NO_UNIFORM_MOMENTS")) {
+        // equal short clips: constant strides, no per-clip table lookups (moments_uniform_kernel)
+        const int T = (int)b->uniform_frames;
+        const int rg = (D + kWarps - 1) / kWarps;
+        int want = (ctx->sm_count * 48 + rg - 1) / rg;               // ~48 CTAs per SM in total
+        int per = (b->n_clips + want - 1) / want;
+        per = std::max(8, (per + 3) / 4 * 4);
+        dim3 grid((unsigned)((b->n_clips + per - 1) / per), (unsigned)rg);
+#define HPSS_UMOMENTS_LAUNCH(MAXC, CLIP)                                                                              \
+        moments_uniform_kernel<MAXC, CLIP><<<grid, kThreads, 0, st>>>(feat, b->n_clips, T, per, D, d_class, n_classes, \
+                                                                      sum, sumsq, count, nonfinite, clip_max,          \
+                                                                      rows_per_stream, n_streams, top_db)
+        if (clip_max) {
+            if (n_classes <= 4) HPSS_UMOMENTS_LAUNCH(4, true); else HPSS_UMOMENTS_LAUNCH(8, true);
+        } else {
+            if (n_classes <= 4) HPSS_UMOMENTS_LAUNCH(4, false); else HPSS_UMOMENTS_LAUNCH(8, false);
+        }
+#undef HPSS_UMOMENTS_LAUNCH
+        HPSS_LAUNCHED("moments_uniform_kernel");
+        return HPSS_OK;
     }
     // frame chunks: multiples of 32 frames, enough CTAs for ~8 waves of 8 resident CTAs per SM
     const int row_groups = ((D + 1) / 2 + kWarps - 1) / kWarps;   // a warp owns two rows

@@ -405,3 +405,34 @@ def test_no_out_of_bounds_writes_canary(ctx):
         assert (big_acc[:32] == -7.0).all() and (big_acc[32 + n_acc:] == -7.0).all()
         ref = engine.featuregram(batch, wave, prm)
         assert torch.equal(ref, out)
+
+
+@pytest.mark.parametrize("T,D,n", [(98, 240, 37), (128, 80, 9), (5, 402, 64)])
+def test_moments_uniform_short_clips(ctx, T, D, n):
+    """Batches of equal short clips take moments_uniform_kernel (constant strides, no table lookups): raw
+    moments against float64 numpy, and the fused top_db clip against hpss_topdb_clip."""
+    rng = np.random.default_rng(T * 1000 + D)
+    fvs = [(rng.standard_normal((D, T)) * 9 - 35).astype(np.float32) for _ in range(n)]
+    cls = [int(c) for c in rng.integers(0, 3, size=n)]
+    batch = engine.Batch(ctx, clip_frames=[T] * n)
+    feat = to_dev(flat_batch(fvs))
+    acc = engine.moments(batch, feat, D, cls, 3).cpu().numpy()
+    X = np.stack(fvs).astype(np.float64)                       # (n, D, T)
+    want_sum = np.stack([X[[i for i in range(n) if cls[i] == k]].sum(axis=(0, 2)) if any(c == k for c in cls)
+                         else np.zeros(D) for k in range(3)])
+    assert np.allclose(acc[:3 * D].reshape(3, D), want_sum, rtol=1e-6, atol=1e-3)
+    assert np.allclose(acc[3 * D:4 * D], (X ** 2).sum(axis=(0, 2)), rtol=1e-6)
+    assert list(acc[4 * D:4 * D + 3]) == [T * sum(1 for c in cls if c == k) for k in range(3)]
+    assert acc[4 * D + 3] == 0
+    # fused clip: two streams of D/2 rows, per-clip / per-stream maxima
+    rps = D // 2
+    mx = X.reshape(n, 2, rps * T).max(axis=2).astype(np.float32)
+    key = np.where(mx.view(np.uint32) & 0x80000000, ~mx.view(np.uint32), mx.view(np.uint32) | 0x80000000).astype(np.uint32)
+    cmax = torch.from_numpy(key.view(np.int32).reshape(-1)).cuda()
+    a = feat.clone()
+    b_ = feat.clone()
+    acc2 = engine.topdb_moments(batch, a, rps, 2, cmax, 30.0, cls, 3).cpu().numpy()
+    engine.topdb_clip(batch, b_, rps, 2, cmax, 30.0)
+    assert torch.equal(a, b_)
+    Xc = b_.cpu().numpy().reshape(n, D, T).astype(np.float64)
+    assert np.allclose(acc2[3 * D:4 * D], (Xc ** 2).sum(axis=(0, 2)), rtol=1e-6)
