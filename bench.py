@@ -250,10 +250,11 @@ def run_gpu(args):
         fused = os.environ.get("HPSS_USE_FUSED", "0") not in ("", "0")     # the path hpss_featuregram takes
         if fused:
             names = ["K1 stft_mag", "K2h median_time", "K2p+K3 perc_mask_mel_log", "K3b+K5 topdb_moments"]
-            bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F + 8 * M, 16 * M]
+            bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F + 8 * M, 8 * M]
         else:
             names = ["K1 stft_mag", "K2h median_time", "K2p median_freq", "K3 mask_mel_log", "K3b+K5 topdb_moments"]
-            bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F, 12 * F + 8 * M, 16 * M]
+            # K3b+K5 reads every feature once and writes back only the values the top_db clip changes: 8*M, not 16*M
+            bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F, 12 * F + 8 * M, 8 * M]
         tot = [0.0] * len(names)
         reps = max(args.steps, 5)
         for it in range(reps + 2):
