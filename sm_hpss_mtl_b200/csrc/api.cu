@@ -360,7 +360,12 @@ static int features_from_spec(hpss_ctx* ctx, const hpss_batch* b, const float* S
         // (opt-in while it is not faster than the two separate kernels: HPSS_USE_FUSED=1)
         static const int use_fused = getenv("HPSS_USE_FUSED") ? atoi(getenv("HPSS_USE_FUSED")) : 0;
         if (use_fused) {
-            if (use_fused != 2 && mp) {   // register walk + mel sweep (k = 15, 31)
+            if (use_fused == 3 && mp) {   // warp-specialised walk + sweep (k = 15, 23, 31)
+                rc = launch_perc_mask_mel_ws(ctx, b, S, harm, rows, p->l_perc, mp, is_log ? 1 : 0, p->amin, out,
+                                             clip ? clip_max : nullptr, st, &fused);
+                if (rc) return rc;
+            }
+            if (!fused && use_fused != 2 && mp) {   // register walk + mel sweep (k = 15, 31)
                 rc = launch_perc_mask_mel_walk(ctx, b, S, harm, rows, p->l_perc, mp, is_log ? 1 : 0, p->amin, out,
                                                clip ? clip_max : nullptr, st, &fused);
                 if (rc) return rc;
@@ -667,7 +672,12 @@ int hpss_perc_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* 
     }
     bool handled = false;
     int rc = HPSS_OK;
-    if (mp && !getenv("HPSS_NO_WALK")) {
+    if (mp && getenv("HPSS_WS")) {   // warp-specialised variant (measured slower than the single-warp walk: opt-in)
+        rc = launch_perc_mask_mel_ws(ctx, batch, S, harm, rows, k, mp, log_power, amin, out, clip_max,
+                                     (cudaStream_t)stream, &handled);
+        if (rc) return rc;
+    }
+    if (!handled && mp && !getenv("HPSS_NO_WALK")) {
         rc = launch_perc_mask_mel_walk(ctx, batch, S, harm, rows, k, mp, log_power, amin, out, clip_max,
                                        (cudaStream_t)stream, &handled);
         if (rc) return rc;

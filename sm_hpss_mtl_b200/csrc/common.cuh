@@ -132,6 +132,9 @@ int launch_median_freq_walk(hpss_ctx* ctx, const hpss_batch* b, const float* S, 
 int launch_perc_mask_mel_walk(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, int rows, int k,
                               const MelPlan* mel, int log_power, float amin, float* out, uint32_t* clip_max,
                               cudaStream_t st, bool* handled);
+int launch_perc_mask_mel_ws(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, int rows, int k,
+                            const MelPlan* mel, int log_power, float amin, float* out, uint32_t* clip_max,
+                            cudaStream_t st, bool* handled);
 int launch_mel_bands(const float* mel, int n_mels, int rows, int2* band, cudaStream_t st);
 int launch_topdb(hpss_ctx* ctx, const hpss_batch* b, float* out, int rows_per_stream, int n_streams,
                  const uint32_t* clip_max, float top_db, cudaStream_t st);

@@ -371,12 +371,19 @@ def test_perc_mask_mel_fused_equals_separate_kernels(ctx, k, n_fft, n_mels, Ts):
     perc = engine.median_freq(batch, S, F, k)
     for c, m in enumerate(mats):                           # the walk kernel itself: bit-exact against scipy
         assert np.array_equal(batch.clip(perc, F, c).cpu().numpy(), lr.median_filter_scipy(m, k, axis=0))
+    import os
     for log_power in (0, 1):
         want, cm_w = engine.mask_mel_log(batch, S, harm, perc, F, mel_sr=22050, n_mels=n_mels, log_power=bool(log_power))
-        got, cm_g = engine.perc_mask_mel_log(batch, S, harm, F, k, 22050, n_mels, log_power=log_power)
-        assert torch.equal(got, want)
-        if log_power:
-            assert torch.equal(cm_g, cm_w)
+        for ws in (False, True):                       # single-warp walk / warp-specialised producer-consumer variant
+            if ws:
+                os.environ["HPSS_WS"] = "1"
+            try:
+                got, cm_g = engine.perc_mask_mel_log(batch, S, harm, F, k, 22050, n_mels, log_power=log_power)
+            finally:
+                os.environ.pop("HPSS_WS", None)
+            assert torch.equal(got, want), (ws, log_power)
+            if log_power:
+                assert torch.equal(cm_g, cm_w)
 
 
 def test_no_out_of_bounds_writes_canary(ctx):
