@@ -269,6 +269,9 @@ static int make_batch(hpss_ctx* ctx, const std::vector<int64_t>& samples, const 
     b->uniform_frames = (n > 0) ? frames[0] : 0;
     for (int c = 1; c < n; ++c)
         if (frames[c] != frames[0]) { b->uniform_frames = 0; break; }
+    b->uniform_samples = (n > 0 && has_samples) ? samples[0] : 0;
+    for (int c = 1; c < n && b->uniform_samples; ++c)
+        if (samples[c] != samples[0]) b->uniform_samples = 0;
     // clip of the first frame of every 32-frame block (empty clips are skipped)
     const int64_t total = b->frame_off[n];
     std::vector<int32_t> block_clip((size_t)((total + 31) / 32) + 1, 0);

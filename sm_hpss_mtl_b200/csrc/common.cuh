@@ -89,6 +89,7 @@ struct hpss_batch {
     std::vector<int64_t> frame_off;    // n_clips + 1
     int64_t max_frames = 0;
     int64_t uniform_frames = 0;        // T when every clip has exactly T frames, else 0
+    int64_t uniform_samples = 0;       // L when every clip has exactly L samples, else 0
     int64_t* d_sample_off = nullptr;
     int64_t* d_frame_off = nullptr;
     int32_t* d_block_clip = nullptr;   // clip of the first frame of every 32-frame block of the batch

@@ -22,6 +22,9 @@ namespace hpss {
 
 namespace {
 
+#ifndef HPSS_K3_U
+#define HPSS_K3_U 4      // frequency rows in flight per warp in the sweep kernel
+#endif
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kFCsplit = 64;    // frequency rows staged per chunk when a whole column does not fit
@@ -407,10 +410,10 @@ int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const fl
         const int64_t n_warps = (total + 31) / 32;
         const unsigned grid = (unsigned)((n_warps + kWarps - 1) / kWarps);
         if (log_power)
-            mask_mel_sweep2_kernel<4, 1><<<grid, kThreads, 0, st>>>(S, harm, perc, b->d_frame_off, b->d_block_clip, total, rows,
+            mask_mel_sweep2_kernel<HPSS_K3_U, 1><<<grid, kThreads, 0, st>>>(S, harm, perc, b->d_frame_off, b->d_block_clip, total, rows,
                                                                     emit4, sweep_w, n_mels, amin, out, clip_max);
         else
-            mask_mel_sweep2_kernel<4, 0><<<grid, kThreads, 0, st>>>(S, harm, perc, b->d_frame_off, b->d_block_clip, total, rows,
+            mask_mel_sweep2_kernel<HPSS_K3_U, 0><<<grid, kThreads, 0, st>>>(S, harm, perc, b->d_frame_off, b->d_block_clip, total, rows,
                                                                     emit4, sweep_w, n_mels, amin, out, clip_max);
         HPSS_LAUNCHED("mask_mel_sweep2_kernel");
         return HPSS_OK;

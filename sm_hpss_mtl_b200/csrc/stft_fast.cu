@@ -13,6 +13,8 @@
 //   * lane = frame everywhere (half-warps of 16 frames): the frame stride of the spectrum buffer (N2 + 1
 //     float2) and of the padded sample staging ((hop + pad)/2 float2, pad chosen so that it is odd) make every
 //     shared-memory access conflict free, and the magnitudes leave as 64-byte runs of one frequency row.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "fft_codelets_gen.cuh"
 
@@ -25,6 +27,17 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+
+// Batches of equal clips whose length is a multiple of the hop: frame t of clip c starts at sample
+// (c * fpc + t) * hop, so the batch is one long signal in which the "virtual" frames t >= T of every clip are
+// skipped; tiles then hold 16 consecutive virtual frames regardless of clip borders (T = 98: 98 % of the lanes
+// busy instead of 14 of 16).  fpc = 0: per-clip tile list.
+struct UniformBatch {
+    int fpc;                 // virtual frames per clip = clip samples / hop
+    int T;                   // real frames per clip
+    int n_clips;
+    int64_t total_samples;
+};
 
 template <int NFFT, int HOP, int NA, int NB, int NT>
 struct FastCfg {
@@ -48,7 +61,8 @@ __global__ void __launch_bounds__(NT)
 stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sample_off,
                  const int64_t* __restrict__ frame_off, const int2* __restrict__ tiles,
                  const float* __restrict__ window, const float2* __restrict__ tw_half,
-                 const float2* __restrict__ tw_full, int power, float* __restrict__ S, float2* __restrict__ cplx) {
+                 const float2* __restrict__ tw_full, int power, float* __restrict__ S, float2* __restrict__ cplx,
+                 UniformBatch uni) {
     using C = FastCfg<NFFT, HOP, NA, NB, NT>;
     constexpr int N2 = C::N2, ZS = C::ZS, PAD = C::PAD, HOPP = C::HOPP, G = C::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -59,11 +73,34 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
     float* s_samp = s_win + NFFT;                               // padded: sample s at s + PAD * (s / HOP)
 
     const int tid = threadIdx.x;
-    const int2 tile = tiles[blockIdx.x];
-    const int c = tile.x, t0 = tile.y;
-    const int64_t fo = frame_off[c];
-    const int T = (int)(frame_off[c + 1] - fo);
-    const int nf = min(C::TT, T - t0);
+    const int fr = tid & 15;
+    const int g = tid >> 4;
+    int T, seg;
+    int64_t base;                  // element offset of (bin 0, this lane's frame) in S
+    bool live;
+    const float* src;
+    if (uni.fpc > 0) {
+        const int64_t v0 = (int64_t)blockIdx.x * C::TT;
+        src = wave + v0 * HOP;
+        const int64_t left = uni.total_samples - v0 * HOP;
+        seg = (int)(left < (int64_t)C::SEG ? left : (int64_t)C::SEG);
+        const int64_t v = v0 + fr;
+        const int c = (int)(v / uni.fpc);
+        const int t = (int)(v - (int64_t)c * uni.fpc);
+        T = uni.T;
+        live = c < uni.n_clips && t < T;
+        base = (int64_t)(N2 + 1) * ((int64_t)c * T) + t;
+    } else {
+        const int2 tile = tiles[blockIdx.x];
+        const int c = tile.x, t0 = tile.y;
+        const int64_t fo = frame_off[c];
+        T = (int)(frame_off[c + 1] - fo);
+        const int nf = min(C::TT, T - t0);
+        src = wave + sample_off[c] + (int64_t)t0 * HOP;
+        seg = (nf - 1) * HOP + NFFT;
+        live = fr < nf;
+        base = (int64_t)(N2 + 1) * fo + t0 + fr;
+    }
 
     // ---- stage tables and the sample segment
     // window x 0.5 (exact): the spectrum buffer then holds Z/2 and the unpack needs no halving
@@ -74,8 +111,6 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
     for (int i = tid; i < N2; i += NT) s_twh[i] = __ldg(tw_half + i);
     for (int i = tid; i <= N2 / 2; i += NT) s_twf[i] = __ldg(tw_full + i);
     {
-        const float* src = wave + sample_off[c] + (int64_t)t0 * HOP;
-        const int seg = (nf - 1) * HOP + NFFT;
         if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
             const float4* src4 = reinterpret_cast<const float4*>(src);
             for (int i = tid; i < seg / 4; i += NT) {
@@ -90,10 +125,6 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
         }
     }
     __syncthreads();
-
-    const int fr = tid & 15;
-    const int g = tid >> 4;
-    const bool live = fr < nf;
 
     // ---- pass 1: DFT-NA over q of w[n] x[n], n = NB*q + b  ->  Y[b][k1] at NA*b + k1
     if (live) {
@@ -142,9 +173,7 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
     // ---- real-FFT unpack + magnitude, written (f, t) with lanes along t.  Bins k and N2-k share their loads:
     // X[k] = E + W*O and X[N2-k] = conj(E - W*O) with E, O from Z[k] and conj(Z[N2-k]).
     if (live) {
-        const int F = N2 + 1;
         const float2* zrow = Z + fr * ZS;
-        const int64_t base = (int64_t)F * fo + t0 + fr;
         char* Sg = reinterpret_cast<char*>(S + base);
         const int T4 = 4 * T;                              // row pitch in bytes: one IMAD.WIDE per address
         // one bin pair: X[k] = E + W*O, X[N2-k] = conj(E - W*O), E = Z[k] + conj(Z[N2-k]), O = -i (Z[k] - conj(Z[N2-k]))
@@ -199,21 +228,35 @@ int launch_cfg(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* p
         set_error("n_fft=%d does not fit the shared-memory FFT (max %d bytes)", NFFT, ctx->max_smem_optin);
         return HPSS_ERR_UNSUPPORTED;
     }
-    // tile height: at most 16 frames, an even split of the longest clip
-    int tt = C::TT;
-    if (b->max_frames > 0) {
-        const int64_t nt = (b->max_frames + tt - 1) / tt;
-        tt = (int)((b->max_frames + nt - 1) / nt);
-    }
-    int rc = ensure_stft_tiles(b, tt);
-    if (rc) return rc;
-    if (b->n_stft_tiles == 0) return HPSS_OK;
     // MODE 0: magnitudes only (the feature path); MODE 1: power and / or complex output as well
     auto kern = (power || cplx) ? stft_fast_kernel<NFFT, HOP, NA, NB, NT, 1> : stft_fast_kernel<NFFT, HOP, NA, NB, NT, 0>;
     HPSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
-    kern<<<b->n_stft_tiles, NT, C::smem_bytes, st>>>(wave, b->d_sample_off, b->d_frame_off, b->d_stft_tiles,
-                                                     plan->d_window, plan->d_tw_half, plan->d_tw_full, power, S,
-                                                     reinterpret_cast<float2*>(cplx));
+    UniformBatch uni{0, 0, 0, 0};
+    const int64_t L = b->uniform_samples;
+    if (L > 0 && L % HOP == 0 && b->uniform_frames > 0 && L / HOP < 0x7fffffff && !getenv("HPSS_NO_UNIFORM_STFT")) {
+        // equal clips, length a multiple of the hop: 16 consecutive virtual frames per tile, across clip borders
+        uni.fpc = (int)(L / HOP);
+        uni.T = (int)b->uniform_frames;
+        uni.n_clips = b->n_clips;
+        uni.total_samples = b->sample_off[b->n_clips];
+        const int64_t n_tiles = ((int64_t)b->n_clips * uni.fpc + C::TT - 1) / C::TT;
+        kern<<<(unsigned)n_tiles, NT, C::smem_bytes, st>>>(wave, b->d_sample_off, b->d_frame_off, nullptr, plan->d_window,
+                                                           plan->d_tw_half, plan->d_tw_full, power, S,
+                                                           reinterpret_cast<float2*>(cplx), uni);
+    } else {
+        // tile height: at most 16 frames, an even split of the longest clip
+        int tt = C::TT;
+        if (b->max_frames > 0) {
+            const int64_t nt = (b->max_frames + tt - 1) / tt;
+            tt = (int)((b->max_frames + nt - 1) / nt);
+        }
+        int rc = ensure_stft_tiles(b, tt);
+        if (rc) return rc;
+        if (b->n_stft_tiles == 0) return HPSS_OK;
+        kern<<<b->n_stft_tiles, NT, C::smem_bytes, st>>>(wave, b->d_sample_off, b->d_frame_off, b->d_stft_tiles,
+                                                         plan->d_window, plan->d_tw_half, plan->d_tw_full, power, S,
+                                                         reinterpret_cast<float2*>(cplx), uni);
+    }
     HPSS_LAUNCHED("stft_fast_kernel");
     return HPSS_OK;
 }
