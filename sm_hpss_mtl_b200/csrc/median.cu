@@ -800,23 +800,19 @@ int launch_median(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, 
         HPSS_CUDA(cudaMemcpyAsync(out, S, sizeof(float) * (size_t)rows * total_frames, cudaMemcpyDeviceToDevice, st));
         return HPSS_OK;
     }
-    if (!time_axis) {   // register walk (no shared-memory staging) where k has a stateful step network
-        static const bool no_walk = getenv("HPSS_NO_WALK") != nullptr;   // development knob
+    if (!time_axis) {
+        // frequency axis: register walk, no shared-memory staging (median_walk.cu), every generated kernel size
         bool handled = false;
-        if (!no_walk) {
-            const int rc = launch_median_freq_walk(ctx, b, S, rows, k, out, st, &handled);
-            if (rc || handled) return rc;
-        }
-    }
+        const int rc = launch_median_freq_walk(ctx, b, S, rows, k, out, st, &handled);
+        if (rc || handled) return rc;
+    } else {
 #define HPSS_DISPATCH_K(KK)                                                                                   \
-    if (k == KK) {                                                                                            \
-        return time_axis ? launch_fast<KK, true>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines,      \
-                                                 max_len, uniform_T, st)                                      \
-                         : launch_fast<KK, false>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines,     \
-                                                  max_len, 0, st);                                            \
-    }
-    HPSS_MEDIAN_FAST_KS(HPSS_DISPATCH_K)
+        if (k == KK)                                                                                          \
+            return launch_fast<KK, true>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines, max_len, \
+                                         uniform_T, st);
+        HPSS_MEDIAN_FAST_KS(HPSS_DISPATCH_K)
 #undef HPSS_DISPATCH_K
+    }
     return time_axis ? launch_generic<true>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines, max_len, k, st)
                      : launch_generic<false>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines, max_len, k, st);
 }

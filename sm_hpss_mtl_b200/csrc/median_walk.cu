@@ -24,6 +24,9 @@ namespace hpss {
 
 namespace {
 
+#ifndef HPSS_WALK_MINB
+#define HPSS_WALK_MINB 4
+#endif
 constexpr int kWalkWarps = 4;
 
 // p + i * pitch_bytes as ONE IMAD.WIDE.U32 (FMA pipe): the ALU pipe belongs to the FMNMX stream
@@ -48,7 +51,7 @@ struct WalkArgs {
 };
 
 template <int K, bool FUSED, int LOGP>
-__global__ void __launch_bounds__(kWalkWarps * 32, (FUSED || K > 35) ? (K > 47 ? 2 : 3) : 4)
+__global__ void __launch_bounds__(kWalkWarps * 32, (FUSED || K > 35) ? (K > 47 ? 2 : 3) : HPSS_WALK_MINB)
 median_freq_walk_kernel(WalkArgs a, const int64_t* __restrict__ frame_off, const int32_t* __restrict__ block_clip,
                         int64_t total_frames, int rows) {
     using Step = MedianStep<K>;
