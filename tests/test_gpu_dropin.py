@@ -197,3 +197,38 @@ def test_ragged_batch_musan_like(ctx):
         want = po.featuregram(y, 16000, 25, 10, 21, 11, 400, 120, "LogMelHarmPercSpec")
         got = batch.clip(out, 240, c).cpu().numpy()
         assert got.shape == want.shape and rel_l2(got, want) < TOL, c
+
+
+def test_one_hour_stream_full_size(ctx):
+    """BASELINE.json configs[3] at full size: one 1-hour 16 kHz stream, n_fft 2048, hop 512, k = 31
+    (112 497 frames x 1025 bins).  Medians bit-exact against scipy on row / column subsets (time-axis tiles
+    with halos, frequency walk with 65 steps), STFT against the oracle on a slice, features finite and
+    consistent with the top_db floor."""
+    L = 57_600_000
+    g = torch.Generator(device="cuda").manual_seed(7)
+    wave = torch.randn(L, generator=g, device="cuda") * 0.3
+    wave += 0.5 * torch.sin(torch.arange(L, device="cuda", dtype=torch.float32) * (2 * np.pi * 440.0 / 16000))
+    wave /= wave.abs().max()
+    batch = engine.Batch(ctx, clip_lengths=[L], n_fft=2048, hop_length=512)
+    T = batch.total_frames
+    assert T == 1 + (L - 2048) // 512 == 112497
+    S = engine.stft_mag(batch, wave, 2048, 2048, 512)
+    harm = engine.median_time(batch, S, 1025, 31).view(1025, T)
+    perc = engine.median_freq(batch, S, 1025, 31).view(1025, T)
+    Sv = S.view(1025, T)
+    rows = [0, 1, 511, 1024]
+    Sr = Sv[rows].cpu().numpy()
+    assert np.array_equal(harm[rows].cpu().numpy(), lr.median_filter_scipy(Sr, 31, axis=1))
+    cols = slice(56000, 56300)
+    Sc = Sv[:, cols].cpu().numpy()
+    assert np.array_equal(perc[:, cols].cpu().numpy(), lr.median_filter_scipy(Sc, 31, axis=0))
+    # STFT of a slice of the stream against the oracle (frame indexing at a large offset)
+    t0 = 100_000
+    y = wave[t0 * 512:t0 * 512 + 2048 + 512 * 63].cpu().numpy()
+    want = np.abs(lr.stft(y, n_fft=2048, hop_length=512, win_length=2048))
+    assert rel_l2(Sv[:, t0:t0 + 64].cpu().numpy(), want) < TOL
+    prm = engine.make_params(n_fft=2048, win_length=2048, hop_length=512, l_harm=31, l_perc=31, n_mels=120)
+    out = engine.featuregram(batch, wave, prm).view(2, 120, T)
+    assert torch.isfinite(out).all()
+    mx, mn = out.amax(dim=(1, 2)), out.amin(dim=(1, 2))
+    assert (mn >= mx - 80.0 - 1e-3).all()
