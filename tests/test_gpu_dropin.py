@@ -232,3 +232,29 @@ def test_one_hour_stream_full_size(ctx):
     assert torch.isfinite(out).all()
     mx, mn = out.amax(dim=(1, 2)), out.amin(dim=(1, 2))
     assert (mn >= mx - 80.0 - 1e-3).all()
+
+
+@pytest.mark.parametrize("n_fft", [512, 1024, 2048])
+@pytest.mark.parametrize("k", [17, 31, 63])
+def test_sweep_config_parity(ctx, n_fft, k):
+    """BASELINE.json configs[4]: n_fft in {512, 1024, 2048} (hop n_fft/4) x median kernel in {17, 31, 63}:
+    medians bit-exact against scipy, features against the oracle, two ragged clips per case."""
+    hop = n_fft // 4
+    Ls = [3 * 16000 + 123, 16000]
+    waves = [synth.synth_clip(900 + i, L) for i, L in enumerate(Ls)]
+    batch = engine.Batch(ctx, clip_lengths=Ls, n_fft=n_fft, hop_length=hop)
+    wave = torch.from_numpy(np.concatenate(waves)).cuda()
+    F = n_fft // 2 + 1
+    S = engine.stft_mag(batch, wave, n_fft, n_fft, hop)
+    harm = engine.median_time(batch, S, F, k)
+    perc = engine.median_freq(batch, S, F, k)
+    prm = engine.make_params(n_fft=n_fft, win_length=n_fft, hop_length=hop, l_harm=k, l_perc=k, n_mels=120)
+    out = engine.featuregram(batch, wave, prm)
+    frame_ms, hop_ms = n_fft / 16.0, hop / 16.0
+    for c, y in enumerate(waves):
+        Sc = batch.clip(S, F, c).cpu().numpy()
+        assert np.array_equal(batch.clip(harm, F, c).cpu().numpy(), lr.median_filter_scipy(Sc, k, axis=1))
+        assert np.array_equal(batch.clip(perc, F, c).cpu().numpy(), lr.median_filter_scipy(Sc, k, axis=0))
+        want = po.featuregram(y, 16000, frame_ms, hop_ms, k, k, n_fft, 120, "LogMelHarmPercSpec")
+        got = batch.clip(out, 240, c).cpu().numpy()
+        assert got.shape == want.shape and rel_l2(got, want) < TOL, (c, rel_l2(got, want))
