@@ -156,6 +156,32 @@ def cpu_baseline_block(args):
                       f"workers ({t:.1f} s of wall time); oracle = librosa algorithm on scipy/numpy"}
 
 
+def bind_to_gpu_numa_node(local):
+    """Best effort: run this rank (and first-touch its pinned host buffers) on the CPUs of the NUMA node its GPU
+    hangs off, so that the H2D / D2H traffic of the e2e leg does not cross the socket interconnect."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{dev}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ============================================================================= GPU arm
 def run_gpu(args):
     import numpy as np
@@ -170,6 +196,7 @@ def run_gpu(args):
         cpu_base = cpu_baseline_block(args)        # before CUDA is initialised in this process
 
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from sm_hpss_mtl_b200 import engine, synth
@@ -307,7 +334,8 @@ def run_gpu(args):
                                + (" + NCCL all-reduce of the 968-double moment vector" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(wave_host.nbytes),
                     "d2h_bytes_per_step": int(out_host.nbytes), "steps": e2e_steps,
-                    "api": "hpss_featuregram_host (pinned host buffers, chunked H2D/compute/D2H pipeline)"},
+                    "api": "hpss_featuregram_host (pinned host buffers, chunked H2D/compute/D2H pipeline)",
+                    "rank0_numa_node": numa_node},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
         }
         if cpu_base is not None:
