@@ -83,6 +83,9 @@ STFT_CASES = [
     (400, 400, 160, [16000]), (400, 400, 160, [16000, 400, 559, 560, 3000]),
     (512, 400, 160, [16000, 8000]), (512, 512, 128, [9000]), (1024, 1024, 256, [20000]),
     (2048, 2048, 512, [40000]), (240, 200, 80, [5000]), (600, 600, 150, [7000]),
+    # batches of equal clips whose length is a multiple of the hop: tiles of 16 virtual frames across clip borders
+    (400, 400, 160, [16000] * 5), (512, 400, 160, [16000] * 3), (512, 512, 128, [12800] * 4),
+    (1024, 1024, 256, [25600] * 3), (2048, 2048, 512, [51200] * 2), (400, 400, 160, [480] * 7),
 ]
 
 
@@ -412,6 +415,22 @@ def test_no_out_of_bounds_writes_canary(ctx):
         assert (big_acc[:32] == -7.0).all() and (big_acc[32 + n_acc:] == -7.0).all()
         ref = engine.featuregram(batch, wave, prm)
         assert torch.equal(ref, out)
+
+
+def test_moments_uniform_more_than_four_classes(ctx):
+    """moments_uniform_kernel with 6 classes (the 8-class instantiation)."""
+    rng = np.random.default_rng(77)
+    T, D, n, nc = 98, 64, 50, 6
+    fvs = [(rng.standard_normal((D, T)) * 4 - 20).astype(np.float32) for _ in range(n)]
+    cls = [int(c) for c in rng.integers(0, nc, size=n)]
+    batch = engine.Batch(ctx, clip_frames=[T] * n)
+    acc = engine.moments(batch, to_dev(flat_batch(fvs)), D, cls, nc).cpu().numpy()
+    X = np.stack(fvs).astype(np.float64)
+    for k in range(nc):
+        idx = [i for i in range(n) if cls[i] == k]
+        want = X[idx].sum(axis=(0, 2)) if idx else np.zeros(D)
+        assert np.allclose(acc[k * D:(k + 1) * D], want, rtol=1e-6, atol=1e-3)
+    assert np.allclose(acc[nc * D:(nc + 1) * D], (X ** 2).sum(axis=(0, 2)), rtol=1e-6)
 
 
 @pytest.mark.parametrize("T,D,n", [(98, 240, 37), (128, 80, 9), (5, 402, 64)])
