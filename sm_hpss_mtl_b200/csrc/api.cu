@@ -564,6 +564,7 @@ int hpss_batch_destroy(hpss_batch* b) {
     if (b->d_block_clip) cudaFree(b->d_block_clip);
     if (b->d_stft_tiles) cudaFree(b->d_stft_tiles);
     if (b->d_clip_class) cudaFree(b->d_clip_class);
+    for (auto& kv : b->time_tiles) if (kv.second.first) cudaFree(kv.second.first);
     for (auto* s : b->host_chunks) hpss_batch_destroy(s);
     delete b;
     return HPSS_OK;

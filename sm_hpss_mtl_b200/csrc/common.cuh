@@ -98,6 +98,9 @@ struct hpss_batch {
     int n_stft_tiles = 0;
     int2* d_stft_tiles = nullptr;
     int32_t* d_clip_class = nullptr;   // scratch for hpss_moments
+    // K2h tile lists of ragged batches, one per (rows, tile length): the (line block, first position) pairs that
+    // actually exist (a grid over the longest clip would be mostly empty for MUSAN-shaped length distributions)
+    std::map<std::pair<int, int>, std::pair<int2*, int64_t>> time_tiles;
     // clip chunks of the pipelined host entry (built on first use, owned by this batch)
     std::vector<int> host_cut;
     std::vector<hpss_batch*> host_chunks;

@@ -99,13 +99,24 @@ template <bool TIME_AXIS>
 __device__ __forceinline__ void tile_store(const float* __restrict__ sm, float* __restrict__ out, const LineInfo& li,
                                            int lane, int p0, int TT, int lstride) {
     if (TIME_AXIS) {
-        const int n0 = __shfl_sync(0xffffffffu, li.n, 0);
-        if (__all_sync(0xffffffffu, li.n == n0)) {
-            // uniform lengths: line r starts r*n0 elements after line 0
-            if (n0 == 0 || p0 >= n0) return;
+        // runs of rows with the same length (see tile_fill_async): one or two per block in practice
+        const int nA = __shfl_sync(0xffffffffu, li.n, 0);
+        const unsigned sameA = __ballot_sync(0xffffffffu, li.n == nA);
+        int rA = 32, rB = 32, nB = nA;
+        unsigned rest = 0;
+        if (sameA != 0xffffffffu) {
+            rA = __ffs(~sameA) - 1;
+            nB = __shfl_sync(0xffffffffu, li.n, rA);
+            const unsigned sameB = __ballot_sync(0xffffffffu, lane < rA || li.n == nB);
+            rB = (sameB == 0xffffffffu) ? 32 : __ffs(~sameB) - 1;
+            rest = __ballot_sync(0xffffffffu, lane >= rB && li.n != 0);
+        }
+        if (rA == 32) {
+            // one run: line r starts r * nA elements after line 0
+            if (nA == 0 || p0 >= nA) return;
             float* row0 = out + __shfl_sync(0xffffffffu, li.base, 0) + p0;
-            const int lim = min(TT, n0 - p0);
-            const uint32_t pitch = 4u * (uint32_t)n0;      // bytes between rows: one IMAD.WIDE.U32 per address (FMA pipe)
+            const int lim = min(TT, nA - p0);
+            const uint32_t pitch = 4u * (uint32_t)nA;      // bytes between rows: one IMAD.WIDE.U32 per address (FMA pipe)
             for (int pos = lane; pos < lim; pos += 32) {
                 const float* s = sm + pos;
                 char* d0 = reinterpret_cast<char*>(row0 + pos);
@@ -113,6 +124,24 @@ __device__ __forceinline__ void tile_store(const float* __restrict__ sm, float* 
                 for (int r = 0; r < 32; ++r, s += lstride)
                     *reinterpret_cast<float*>(d0 + (uint64_t)(uint32_t)r * pitch) = *s;
             }
+            return;
+        }
+        if (rest == 0) {
+            // two runs (the block straddles a clip border)
+            auto store_run = [&](int rb, int re, int n0) {
+                if (rb >= re || n0 == 0 || p0 >= n0) return;
+                float* row0 = out + __shfl_sync(0xffffffffu, li.base, rb) + p0;
+                const int lim = min(TT, n0 - p0);
+                const uint32_t pitch = 4u * (uint32_t)n0;
+                for (int pos = lane; pos < lim; pos += 32) {
+                    const float* s = sm + rb * lstride + pos;
+                    char* d0 = reinterpret_cast<char*>(row0 + pos);
+                    for (int r = 0; r < re - rb; ++r, s += lstride)
+                        *reinterpret_cast<float*>(d0 + (uint64_t)(uint32_t)r * pitch) = *s;
+                }
+            };
+            store_run(0, rA, nA);
+            store_run(rA, rB, nB);
             return;
         }
         for (int r = 0; r < 32; ++r) {
@@ -179,40 +208,56 @@ struct FillCache {   // time axis, uniform batch: reflected source offsets of th
 
 template <bool TIME_AXIS>
 __device__ __forceinline__ void tile_fill_async(uint32_t sm_base, const float* __restrict__ S, const LineInfo& li,
-                                                int lane, int lw, int p0, int halo, int span, int lstride, FillCache& fc) {
+                                                int lane, int lw, int p0, int halo, int span, int lstride, FillCache (&fc)[2]) {
     if (TIME_AXIS) {
         // lanes sweep positions of one row at a time (coalesced); reflected source indices are
         // computed once per lane when all 32 rows have the same length (uniform batch)
-        const int n0 = __shfl_sync(0xffffffffu, li.n, 0);
-        const bool uniform = __all_sync(0xffffffffu, li.n == n0);
-        if (uniform) {
-            if (n0 == 0 || p0 >= n0) return;
-            // equal lengths => consecutive lines are exactly n0 elements apart, also across clips.
-            // The reflected source offsets of this lane's positions depend on (p0, n0) only: they are kept in
-            // registers from tile to tile, so a row costs one address add per 128-byte copy.
+        // Runs of rows with the same length: the 32 lines of a block are consecutive rows, so rows of equal length
+        // are exactly n elements apart (also across clips of equal length).  A block holds one run (inside a
+        // clip, or a uniform batch) or two (it straddles a clip border); anything else takes the slow path below.
+        const int nA = __shfl_sync(0xffffffffu, li.n, 0);
+        const unsigned sameA = __ballot_sync(0xffffffffu, li.n == nA);
+        int rA = 32, rB = 32, nB = nA;
+        unsigned rest = 0;
+        if (sameA != 0xffffffffu) {                             // (warp-uniform) not the common single-run block
+            rA = __ffs(~sameA) - 1;                                               // rows [0, rA) have length nA
+            nB = __shfl_sync(0xffffffffu, li.n, rA);
+            const unsigned sameB = __ballot_sync(0xffffffffu, lane < rA || li.n == nB);
+            rB = (sameB == 0xffffffffu) ? 32 : __ffs(~sameB) - 1;                 // rows [rA, rB) have length nB
+            rest = __ballot_sync(0xffffffffu, lane >= rB && li.n != 0);
+        }
+        if (rest == 0) {                                        // at most two runs (+ absent lines after the batch end)
             constexpr int NCH = FillCache::kChunks;             // span = TT + K - 1 <= 16 * 12 + 62 = 254 < 8 * 32
-            if (fc.p0 != p0 || fc.n0 != n0) {
-                fc.p0 = p0; fc.n0 = n0;
-#pragma unroll
-                for (int q = 0; q < NCH; ++q) fc.off[q] = reflect_idx(p0 - halo + lane + 32 * q, n0);
-            }
-            const float* rowp = S + __shfl_sync(0xffffffffu, li.base, 0) + (int64_t)lw * n0;
             const uint32_t four = 4u * gridDim.y;               // = 4
-            uint32_t drow = sm_base + 4u * (uint32_t)(lw * lstride + lane);
-            const uint32_t dstep = 4u * (uint32_t)(kLoaderWarps * lstride);
-            const int64_t sstep = (int64_t)kLoaderWarps * n0;
-#pragma unroll 2
-            for (int r = lw; r < 32; r += kLoaderWarps, drow += dstep, rowp += sstep) {
+            auto fill_run = [&](int rb, int re, int n0, FillCache& c) {
+                if (rb >= re || n0 == 0 || p0 >= n0) return;            // warp-uniform
+                // The reflected source offsets of this lane's positions depend on (p0, n0) only: they are kept
+                // in registers from tile to tile, so a row costs one address add per 128-byte copy.
+                if (c.p0 != p0 || c.n0 != n0) {
+                    c.p0 = p0; c.n0 = n0;
 #pragma unroll
-                for (int q = 0; q < NCH; ++q) {
-                    // byte address = row + 4 * offset as ONE IMAD.WIDE on the FMA pipe (the multiplier is a
-                    // run-time 4, so the compiler cannot turn it into the two-instruction LEA pair on the ALU
-                    // pipe, which this kernel saturates)
-                    const float* src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(rowp) +
-                                                                      (uint64_t)(uint32_t)fc.off[q] * four);
-                    if (lane + 32 * q < span) cp_async4(drow + 128u * q, src);
+                    for (int q = 0; q < NCH; ++q) c.off[q] = reflect_idx(p0 - halo + lane + 32 * q, n0);
                 }
-            }
+                const int r0 = rb + ((lw - rb) % kLoaderWarps + kLoaderWarps) % kLoaderWarps;   // first row of this warp
+                const float* rowp = S + __shfl_sync(0xffffffffu, li.base, rb) + (int64_t)(r0 - rb) * n0;
+                uint32_t drow = sm_base + 4u * (uint32_t)(r0 * lstride + lane);
+                const uint32_t dstep = 4u * (uint32_t)(kLoaderWarps * lstride);
+                const int64_t sstep = (int64_t)kLoaderWarps * n0;
+#pragma unroll 2
+                for (int r = r0; r < re; r += kLoaderWarps, drow += dstep, rowp += sstep) {
+#pragma unroll
+                    for (int q = 0; q < NCH; ++q) {
+                        // byte address = row + 4 * offset as ONE IMAD.WIDE on the FMA pipe (the multiplier is a
+                        // run-time 4, so the compiler cannot turn it into the two-instruction LEA pair on the
+                        // ALU pipe, which this kernel saturates)
+                        const float* src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(rowp) +
+                                                                          (uint64_t)(uint32_t)c.off[q] * four);
+                        if (lane + 32 * q < span) cp_async4(drow + 128u * q, src);
+                    }
+                }
+            };
+            fill_run(0, rA, nA, fc[0]);
+            if (rA < 32) fill_run(rA, rB, nB, fc[1]);
         } else {
             for (int r = lw; r < 32; r += kLoaderWarps) {
                 const int64_t b = __shfl_sync(0xffffffffu, li.base, r);
@@ -254,7 +299,7 @@ template <int K, bool TIME_AXIS>
 __global__ void __launch_bounds__(kRingThreads, 1)
 median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const int64_t* __restrict__ frame_off,
                    const int32_t* __restrict__ block_clip, int rows, int64_t n_lines, int TT, int n_ptiles,
-                   int64_t n_items, int NB, int uniform_T) {
+                   int64_t n_items, int NB, int uniform_T, const int2* __restrict__ tile_list) {
     constexpr int G = MedianGroup<K>::G;
     constexpr int HALO = K / 2;
     // stateful double steps where K has them (time axis; the frequency axis has its own walk kernel).  MIXED:
@@ -285,28 +330,54 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
     if (warp >= kComputeWarps) {
         // ===== loader warps =====
         const int lw = warp - kComputeWarps;
-        FillCache fc;
+        FillCache fc[2];
+        LineInfo li;
+        li.base = 0; li.n = 0; li.estride = 1;
+        int64_t li_lb = -1;
         for (int64_t n = 0; n < my_items; ++n) {
             const int b = (int)(n % NB);
             const uint32_t use = (uint32_t)(n / NB);
             const int64_t item = blockIdx.x + n * gridDim.x;
-            const int64_t lb = item / n_ptiles;
-            const int p0 = (int)(item - lb * n_ptiles) * TT;
-            const LineInfo li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane, uniform_T);
+            int64_t lb;
+            int p0;
+            if (tile_list != nullptr) {                    // ragged batch: explicit list of the tiles that exist
+                const int2 tl = __ldg(tile_list + item);
+                lb = tl.x; p0 = tl.y;
+            } else {
+                lb = item / n_ptiles;
+                p0 = (int)(item - lb * n_ptiles) * TT;
+            }
+            if (lb != li_lb) {                             // consecutive tiles of a long clip share the line block
+                li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane, uniform_T);
+                li_lb = lb;
+            }
             if (use > 0) mbar_wait(empty0 + 8u * b, (use - 1) & 1u);
             tile_fill_async<TIME_AXIS>(smem_u32(smem + (size_t)b * tile_floats), S, li, lane, lw, p0, HALO, span, lstride, fc);
             cp_async_arrive(full0 + 8u * b);
         }
     } else {
         // ===== compute warps =====
+        LineInfo li;
+        li.base = 0; li.n = 0; li.estride = 1;
+        int64_t li_lb = -1;
         for (int64_t n = warp; n < my_items; n += kComputeWarps) {
             const int b = (int)(n % NB);
             const uint32_t use = (uint32_t)(n / NB);
             float* sm = smem + (size_t)b * tile_floats;
             const int64_t item = blockIdx.x + n * gridDim.x;
-            const int64_t lb = item / n_ptiles;
-            const int p0 = (int)(item - lb * n_ptiles) * TT;
-            const LineInfo li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane, uniform_T);
+            int64_t lb;
+            int p0;
+            if (tile_list != nullptr) {                    // ragged batch: explicit list of the tiles that exist
+                const int2 tl = __ldg(tile_list + item);
+                lb = tl.x; p0 = tl.y;
+            } else {
+                lb = item / n_ptiles;
+                p0 = (int)(item - lb * n_ptiles) * TT;
+            }
+            if (lb != li_lb) {
+                li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane, uniform_T);
+                li_lb = lb;
+            }
             const bool live = li.n > 0 && p0 < li.n;
             mbar_wait(full0 + 8u * b, use & 1u);
             if (live) {
@@ -648,9 +719,37 @@ median_generic_kernel(const float* __restrict__ S, float* __restrict__ out, cons
     }
 }
 
+// (line block, first position) of every time-axis tile that exists in a ragged batch; cached in the batch
+static int time_tile_list(hpss_ctx* ctx, const hpss_batch* cb, int rows, int TT, const int2** d_list, int64_t* n_tiles) {
+    hpss_batch* b = const_cast<hpss_batch*>(cb);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const auto key = std::make_pair(rows, TT);
+    auto it = b->time_tiles.find(key);
+    if (it == b->time_tiles.end()) {
+        std::vector<int2> tiles;
+        const int64_t n_lines = (int64_t)b->n_clips * rows;
+        for (int64_t lb = 0; lb * 32 < n_lines; ++lb) {
+            const int c0 = (int)((lb * 32) / rows);
+            const int c1 = (int)(std::min(n_lines - 1, lb * 32 + 31) / rows);
+            int64_t tmax = 0;
+            for (int c = c0; c <= c1; ++c) tmax = std::max(tmax, b->frame_off[c + 1] - b->frame_off[c]);
+            for (int64_t p0 = 0; p0 < tmax; p0 += TT) tiles.push_back(make_int2((int)lb, (int)p0));
+        }
+        int2* d = nullptr;
+        if (!tiles.empty()) {
+            HPSS_CUDA(cudaMalloc(&d, sizeof(int2) * tiles.size()));
+            HPSS_CUDA(cudaMemcpy(d, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice));
+        }
+        it = b->time_tiles.emplace(key, std::make_pair(d, (int64_t)tiles.size())).first;
+    }
+    *d_list = it->second.first;
+    *n_tiles = it->second.second;
+    return HPSS_OK;
+}
+
 template <int K, bool TIME_AXIS>
-int launch_fast(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_frame_off, const int32_t* d_block_clip, int rows,
-                int64_t n_lines, int64_t max_len, int uniform_T, cudaStream_t st) {
+int launch_fast(hpss_ctx* ctx, const hpss_batch* b, const float* S, float* out, const int64_t* d_frame_off,
+                const int32_t* d_block_clip, int rows, int64_t n_lines, int64_t max_len, int uniform_T, cudaStream_t st) {
     // tile length granule: a stateless group, or a whole stateful double step when its G differs from the group's
     constexpr int G = (TIME_AXIS && MedianStep<K>::available && MedianStep<K>::G != MedianGroup<K>::G)
                           ? 2 * MedianStep<K>::G : MedianGroup<K>::G;
@@ -670,7 +769,14 @@ int launch_fast(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_fram
     TT = (TT + G - 1) / G * G;
     const int n_ptiles = (int)((max_len + TT - 1) / TT);
     const int64_t n_lb = (n_lines + 31) / 32;
-    const int64_t n_items = n_lb * n_ptiles;
+    int64_t n_items = n_lb * n_ptiles;
+    const int2* tile_list = nullptr;
+    if (TIME_AXIS && uniform_T == 0 && n_ptiles > 1 && n_lines < 0x7fffffffLL * 32) {
+        // ragged batch: only the tiles that exist (clips shorter than the longest have fewer)
+        const int rc = time_tile_list(ctx, b, rows, TT, &tile_list, &n_items);
+        if (rc) return rc;
+        if (n_items == 0) return HPSS_OK;
+    }
     const int span = TT + K - 1;
     const size_t tile_bytes = (TIME_AXIS ? (size_t)32 * (span | 1) : (size_t)span * 32) * sizeof(float);
     int NB = (int)(((size_t)ctx->max_smem_optin - 512) / (tile_bytes + 16));
@@ -681,7 +787,7 @@ int launch_fast(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_fram
     int64_t grid = (n_items + kComputeWarps - 1) / kComputeWarps;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
     kern<<<(unsigned)grid, kRingThreads, smem, st>>>(S, out, d_frame_off, d_block_clip, rows, n_lines, TT, n_ptiles,
-                                                     n_items, NB, uniform_T);
+                                                     n_items, NB, uniform_T, tile_list);
     HPSS_LAUNCHED("median_fast_kernel");
     return HPSS_OK;
 }
@@ -808,7 +914,7 @@ int launch_median(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, 
     } else {
 #define HPSS_DISPATCH_K(KK)                                                                                   \
         if (k == KK)                                                                                          \
-            return launch_fast<KK, true>(ctx, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines, max_len, \
+            return launch_fast<KK, true>(ctx, b, S, out, b->d_frame_off, b->d_block_clip, rows, n_lines, max_len, \
                                          uniform_T, st);
         HPSS_MEDIAN_FAST_KS(HPSS_DISPATCH_K)
 #undef HPSS_DISPATCH_K
