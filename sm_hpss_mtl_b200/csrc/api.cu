@@ -763,7 +763,8 @@ int hpss_featuregram_host(hpss_ctx* ctx, const hpss_batch* batch, const float* w
     if (pb->host_cut.empty()) {
         // chunking: ~16 chunks, at least 4 M samples each, never splitting a clip
         const int64_t total_samples = batch->sample_off[n];
-        const int64_t target = std::max<int64_t>(total_samples / 16, 4 << 20);
+        const int n_target = getenv("HPSS_HOST_CHUNKS") ? std::max(1, atoi(getenv("HPSS_HOST_CHUNKS"))) : 16;   // development knob
+        const int64_t target = std::max<int64_t>(total_samples / n_target, 1 << 20);
         std::vector<int> cut(1, 0);
         for (int c = 0; c < n;) {
             int e = c;
