@@ -165,7 +165,10 @@ __device__ __forceinline__ void tile_store(const float* __restrict__ sm, float* 
 // buffers.  The loader warp fills tile n (cp.async, reflected at the clip borders) while the
 // compute warps run the selection networks on earlier tiles; full/empty mbarriers per buffer.
 // Item n of a CTA uses buffer n % NB and is consumed by compute warp n % kComputeWarps.
-constexpr int kComputeWarps = 8;
+#ifndef HPSS_COMPUTE_WARPS
+#define HPSS_COMPUTE_WARPS 8
+#endif
+constexpr int kComputeWarps = HPSS_COMPUTE_WARPS;
 #ifndef HPSS_LOADER_WARPS
 #define HPSS_LOADER_WARPS 4
 #endif
