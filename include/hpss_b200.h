@@ -244,6 +244,19 @@ HPSS_API int hpss_extract_patches(hpss_ctx* ctx, const float* feat_dev, int32_t 
                                   int32_t patch_size, int32_t patch_shift, double* out_dev,
                                   void* stream);
 
+/* ---- extension: MFCC.  The reference has no MFCC / DCT anywhere; BASELINE.json's north_star
+ * names it, so it is offered as what librosa.feature.mfcc would add after the reference's log-mel step
+ * (lib/preprocessing.py:119-120): scipy.fftpack.dct(S_db, axis=0, type=2, norm='ortho')[:n_mfcc] per stream.
+ * Parity is pinned to scipy's DCT, not to the reference.
+ *   feat_dev: (n_streams * rows_per_stream, T_c) float32 per clip in the batch layout (hpss_featuregram output);
+ *   out_dev : (n_streams * n_mfcc, T_c) float32 per clip, same layout; must not alias feat_dev;
+ *   1 <= n_mfcc <= min(rows_per_stream, 64).
+ *   hpss_dct_basis: the (n_mfcc, n_mels) float32 basis itself (host memory), for inspection / tests. */
+HPSS_API int hpss_dct_mfcc(hpss_ctx* ctx, const hpss_batch* batch, const float* feat_dev,
+                           int32_t rows_per_stream, int32_t n_streams, int32_t n_mfcc, float* out_dev,
+                           void* stream);
+HPSS_API int hpss_dct_basis(int32_t n_mels, int32_t n_mfcc, float* out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -262,3 +262,17 @@ def power_to_db(S, ref=1.0, amin=1e-10, top_db=80.0):
             raise ParameterError("top_db must be non-negative")
         log_spec = np.maximum(log_spec, log_spec.max() - top_db)
     return log_spec
+
+
+def dct_ortho(S, n_out=None):
+    """Orthonormal DCT-II along axis 0 in float64: what librosa.feature.mfcc applies to its log-mel input
+    (scipy.fftpack.dct(S, axis=0, type=2, norm='ortho')[:n_mfcc]).  EXTENSION: the reference has no MFCC step, so
+    this restates scipy's published definition and is pinned against scipy.fft.dct in tests/test_oracle.py."""
+    S = np.asarray(S, dtype=np.float64)
+    M = S.shape[0]
+    n_out = M if n_out is None else n_out
+    k = np.arange(n_out)[:, None]
+    m = np.arange(M)[None, :]
+    D = np.sqrt(2.0 / M) * np.cos(np.pi * k * (2 * m + 1) / (2.0 * M))
+    D[0] *= np.sqrt(0.5)
+    return D @ S

@@ -87,6 +87,8 @@ PROTOTYPES = {
     "hpss_row_standardize": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "hpss_num_patches": (_i64, [_i64, _i32, _i32]),
     "hpss_extract_patches": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
+    "hpss_dct_mfcc": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "hpss_dct_basis": (C.c_int, [_i32, _i32, _vp]),
 }
 
 _lib = None

@@ -498,6 +498,7 @@ int hpss_ctx_destroy(hpss_ctx* ctx) {
         cudaFree(kv.second->d_window); cudaFree(kv.second->d_tw_half); cudaFree(kv.second->d_tw_full);
         delete kv.second;
     }
+    for (auto& kv : ctx->dct_plans) cudaFree(kv.second);
     for (auto& kv : ctx->mel_plans) { cudaFree(kv.second->d_w); cudaFree(kv.second->d_band); if (kv.second->d_sweep) cudaFree(kv.second->d_sweep); if (kv.second->d_emit4) cudaFree(kv.second->d_emit4); if (kv.second->d_sweep_w) cudaFree(kv.second->d_sweep_w); delete kv.second; }
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->band_scratch) cudaFree(ctx->band_scratch);
@@ -922,6 +923,22 @@ int hpss_scale_data(hpss_ctx* ctx, const hpss_batch* batch, const float* feat, i
     if (!ctx || !batch || !feat || !mean || !stdev || !out) { set_error("scale_data: NULL argument"); return HPSS_ERR_INVALID; }
     HPSS_CUDA(cudaSetDevice(ctx->device));
     return launch_scale(ctx, batch, feat, D, mean, stdev, eps, out, (cudaStream_t)stream);
+}
+
+int hpss_dct_mfcc(hpss_ctx* ctx, const hpss_batch* batch, const float* feat, int32_t rows_per_stream, int32_t n_streams,
+                  int32_t n_mfcc, float* out, void* stream) {
+    if (!ctx || !batch || !feat || !out || feat == out) { set_error("dct_mfcc: NULL or aliased argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return launch_dct(ctx, batch, feat, rows_per_stream, n_streams, n_mfcc, out, (cudaStream_t)stream);
+}
+
+int hpss_dct_basis(int32_t n_mels, int32_t n_mfcc, float* out) {
+    if (!out || n_mels < 1 || n_mfcc < 1 || n_mfcc > n_mels) { set_error("dct_basis: need 1 <= n_mfcc <= n_mels"); return HPSS_ERR_INVALID; }
+    std::vector<float> t((size_t)n_mels * n_mfcc);
+    build_dct_basis_t(n_mels, n_mfcc, n_mfcc, t.data());
+    for (int k = 0; k < n_mfcc; ++k)
+        for (int m = 0; m < n_mels; ++m) out[(size_t)k * n_mels + m] = t[(size_t)m * n_mfcc + k];
+    return HPSS_OK;
 }
 
 int hpss_row_standardize(hpss_ctx* ctx, const hpss_batch* batch, float* feat, int32_t D, void* stream) {

@@ -66,6 +66,7 @@ struct hpss_ctx {
     std::mutex mu;
     std::map<std::pair<int, int>, hpss::FftPlan*> fft_plans;
     std::map<std::tuple<int, int, int>, hpss::MelPlan*> mel_plans;
+    std::map<std::pair<int, int>, float*> dct_plans;       // (M, n_mfcc) -> device D^T (M x 4*ceil(n_mfcc/4))
     // grow-only device workspace (S, harm, perc, clip_max, band scratch)
     void* ws = nullptr;
     size_t ws_bytes = 0;
@@ -148,6 +149,9 @@ int launch_moments(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D,
 int launch_topdb_moments(hpss_ctx* ctx, const hpss_batch* b, float* feat, int rows_per_stream, int n_streams,
                          const uint32_t* clip_max, float top_db, const int32_t* d_class, int n_classes, double* sum,
                          double* sumsq, double* count, double* nonfinite, cudaStream_t st);
+int launch_dct(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int M, int n_streams, int n_mfcc, float* out,
+               cudaStream_t st);
+void build_dct_basis_t(int M, int n_mfcc, int ncols, float* out);
 int launch_scale(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, const float* mean,
                  const float* stdev, double eps, double* out, cudaStream_t st);
 int launch_row_standardize(hpss_ctx* ctx, const hpss_batch* b, float* feat, int D, cudaStream_t st);

@@ -232,6 +232,25 @@ def topdb_clip(batch: Batch, out: torch.Tensor, rows_per_stream: int, n_streams:
     return out
 
 
+def dct_basis(n_mels: int, n_mfcc: int) -> np.ndarray:
+    """(n_mfcc, n_mels) float32 orthonormal DCT-II basis (scipy.fftpack.dct(type=2, norm='ortho') along the mel axis)."""
+    out = np.empty((n_mfcc, n_mels), dtype=np.float32)
+    check(_lib.load().hpss_dct_basis(int(n_mels), int(n_mfcc), C.c_void_p(out.ctypes.data)))
+    return out
+
+
+def dct_mfcc(batch: Batch, feat: torch.Tensor, rows_per_stream: int, n_streams: int, n_mfcc: int = 20,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Extension (not in the reference): per stream, the first n_mfcc rows of the orthonormal DCT-II along the mel
+    axis of a (n_streams * rows_per_stream, T_c) log-mel featuregram -> (n_streams * n_mfcc, T_c) per clip."""
+    if out is None:
+        out = torch.empty(n_streams * n_mfcc * batch.total_frames, dtype=torch.float32, device=feat.device)
+    check(batch.lib.hpss_dct_mfcc(batch.ctx.handle, batch.handle, _dev_ptr(feat, torch.float32, "feat"),
+                                  int(rows_per_stream), int(n_streams), int(n_mfcc), _dev_ptr(out, torch.float32, "out"),
+                                  _stream_ptr()))
+    return out
+
+
 # ---------------------------------------------------------------------------- fused
 def featuregram(batch: Batch, wave: torch.Tensor, params: Params, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     rows = feature_rows(params)

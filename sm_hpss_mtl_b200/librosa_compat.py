@@ -3,7 +3,7 @@
 Mirrors the argument meaning and error behaviour of the librosa (~0.8) functions that
 lib/preprocessing.py calls, restricted to the configurations on the reference path:
 ``stft(center=False)``, ``hpss(power=2.0, margin=1.0)``, ``melspectrogram``, ``power_to_db``,
-``filters.mel`` (Slaney scale and norm).  Anything else raises NotImplementedError rather than
+``filters.mel`` (Slaney scale and norm), plus ``mfcc`` as an extension the reference does not call.  Anything else raises NotImplementedError rather than
 silently computing something different.
 """
 from __future__ import annotations
@@ -134,5 +134,27 @@ def power_to_db(S, ref=1.0, amin=1e-10, top_db=80.0):
     if top_db is not None:
         engine.topdb_clip(batch, out, rows, 1, cmax, float(top_db))
     res = out.cpu().numpy().reshape(rows, T)
+    batch.close()
+    return res
+
+
+def mfcc(y=None, sr=22050, S=None, n_mfcc=20, dct_type=2, norm="ortho", **kwargs):
+    """librosa.feature.mfcc (an extension: the reference never calls it).  ``S`` is a log-power mel spectrogram
+    (n_mels, T); with ``y`` it is power_to_db(melspectrogram(y, **kwargs)).  Returns
+    scipy.fftpack.dct(S, axis=0, type=2, norm='ortho')[:n_mfcc]."""
+    import torch
+    from . import engine
+    if dct_type != 2 or norm != "ortho":
+        raise NotImplementedError("only dct_type=2, norm='ortho' (librosa's defaults)")
+    if S is None:
+        S = power_to_db(melspectrogram(y=y, sr=sr, **kwargs))
+    S = np.ascontiguousarray(S, dtype=np.float32)
+    n_mels, T = S.shape
+    if not 1 <= n_mfcc <= n_mels:
+        raise ParameterError("n_mfcc must be in [1, n_mels]")
+    ctx = _ctx()
+    batch = engine.Batch(ctx, clip_frames=[T])
+    out = engine.dct_mfcc(batch, torch.from_numpy(S.ravel()).cuda(), n_mels, 1, int(n_mfcc))
+    res = out.cpu().numpy().reshape(int(n_mfcc), T)
     batch.close()
     return res

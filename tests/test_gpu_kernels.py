@@ -462,3 +462,43 @@ def test_moments_uniform_short_clips(ctx, T, D, n):
     assert torch.equal(a, b_)
     Xc = b_.cpu().numpy().reshape(n, D, T).astype(np.float64)
     assert np.allclose(acc2[3 * D:4 * D], (Xc ** 2).sum(axis=(0, 2)), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------ MFCC extension (not in the reference)
+@pytest.mark.parametrize("M,streams,n_mfcc,Ts", [(120, 2, 20, [98, 7, 300, 33]), (21, 1, 13, [64]), (128, 2, 40, [31, 1, 2]),
+                                                 (120, 2, 64, [50]), (16, 3, 16, [40, 90])])
+def test_dct_mfcc_matches_scipy(ctx, M, streams, n_mfcc, Ts):
+    import scipy.fft
+    rng = np.random.default_rng(M + n_mfcc)
+    mats = [(rng.standard_normal((streams * M, T)) * 25 - 40).astype(np.float32) for T in Ts]
+    batch = engine.Batch(ctx, clip_frames=Ts)
+    out = engine.dct_mfcc(batch, to_dev(flat_batch(mats)), M, streams, n_mfcc)
+    torch.cuda.synchronize()
+    for c, got in enumerate(batch.split(out, streams * n_mfcc)):
+        x = mats[c].astype(np.float64).reshape(streams, M, -1)
+        want = scipy.fft.dct(x, axis=1, type=2, norm="ortho")[:, :n_mfcc].reshape(streams * n_mfcc, -1)
+        assert np.array_equal(lr.dct_ortho(x[0], n_mfcc), want[:n_mfcc]) or rel_l2(lr.dct_ortho(x[0], n_mfcc), want[:n_mfcc]) < 1e-12
+        r = rel_l2(got.cpu().numpy(), want)
+        assert r < 1e-6, f"clip {c}: rel-L2 {r:.3e}, max-abs {np.abs(got.cpu().numpy() - want).max():.3e}"
+
+
+def test_dct_mfcc_argument_errors(ctx):
+    batch = engine.Batch(ctx, clip_frames=[10])
+    x = torch.zeros(40 * 10, device="cuda")
+    with pytest.raises(Exception):
+        engine.dct_mfcc(batch, x, 40, 1, 41)
+    with pytest.raises(Exception):
+        engine.dct_mfcc(batch, x, 40, 1, 20, out=x)          # aliasing
+
+
+def test_mfcc_of_hpss_featuregram_end_to_end(ctx):
+    """waveform -> HPSS log-mel featuregram (reference path) -> MFCC per stream, against the oracle + scipy."""
+    import scipy.fft
+    y = synth.synth_clip(7, 16000)
+    prm = engine.make_params(n_fft=400, win_length=400, hop_length=160, l_harm=21, l_perc=11, n_mels=120)
+    batch = engine.Batch(ctx, clip_lengths=[len(y)], n_fft=400, hop_length=160)
+    feat = engine.featuregram(batch, to_dev(y.astype(np.float32)), prm)
+    got = engine.dct_mfcc(batch, feat, 120, 2, 20).cpu().numpy().reshape(40, -1)
+    fv = po.featuregram(y, 16000, 25, 10, 21, 11, 400, 120, "LogMelHarmPercSpec")
+    want = scipy.fft.dct(fv.astype(np.float64).reshape(2, 120, -1), axis=1, type=2, norm="ortho")[:, :20].reshape(40, -1)
+    assert rel_l2(got, want) < REL_L2_TOL

@@ -216,3 +216,16 @@ def test_moments_allreduce_gloo_world2():
     want_mean, want_std, n0, n1, n2 = po.get_data_stats(groups, names)
     assert [int(c) for c in counts] == [n0, n1, n2]
     assert np.allclose(mean, want_mean, rtol=1e-6, atol=1e-6) and np.allclose(std, want_std, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("M,n", [(120, 20), (21, 21), (128, 13)])
+def test_dct_basis_table_vs_scipy(M, n):
+    """hpss_dct_basis (host-side table, no GPU needed) against scipy's orthonormal DCT-II of the identity."""
+    import scipy.fft
+    from sm_hpss_mtl_b200 import engine
+    want = scipy.fft.dct(np.eye(M), axis=0, type=2, norm="ortho")[:n]
+    got = engine.dct_basis(M, n)
+    assert got.shape == (n, M) and got.dtype == np.float32
+    assert np.abs(got - want).max() < 1e-7
+    with pytest.raises(Exception):
+        engine.dct_basis(M, M + 1)

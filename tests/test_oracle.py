@@ -207,3 +207,15 @@ def test_hpss_uses_scipy_and_own_median_identically():
     H1, P1 = lr.hpss(S, kernel_size=(21, 11), use_scipy=True)
     H2, P2 = lr.hpss(S, kernel_size=(21, 11), use_scipy=False)
     assert np.array_equal(H1, H2) and np.array_equal(P1, P2)
+
+
+# ------------------------------------------------------------------------------ MFCC extension (not in the reference)
+@pytest.mark.parametrize("M,n", [(120, 20), (21, 13), (128, 40), (7, 7)])
+def test_dct_restatement_vs_scipy(M, n):
+    """Parity pin of the MFCC extension: scipy's own orthonormal DCT-II (what librosa.feature.mfcc calls)."""
+    import scipy.fft
+    rng = np.random.default_rng(M)
+    S = rng.standard_normal((M, 33)) * 30 - 40
+    want = scipy.fft.dct(S, axis=0, type=2, norm="ortho")[:n]
+    got = lr.dct_ortho(S, n)
+    assert np.allclose(got, want, rtol=0, atol=1e-10 * np.abs(want).max())
