@@ -9,6 +9,7 @@
 // the basis D^T (M x n_mfcc, float32 from a float64 evaluation) sits in shared memory and is read as
 // broadcast float4s.  fp32 FMA in increasing m; M x n_mfcc is far too small for tensor-core tiles to pay.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -20,47 +21,80 @@ namespace {
 
 constexpr int kDctThreads = 128;
 constexpr int kDctWarps = kDctThreads / 32;
+constexpr int kRows = 8;               // mel rows per load batch
 constexpr int kMaxMfcc = 64;           // accumulators per lane (registers)
 
-template <int NC4>   // n_mfcc rounded up to a multiple of 4, divided by 4
+// NC4: n_mfcc rounded up to a multiple of 4, divided by 4.  COLS: streams per lane (2 = the harmonic and the
+// percussive column of one frame share every basis read; halves the shared-memory traffic per FFMA).
+template <int NC4, int COLS>
 __global__ void __launch_bounds__(kDctThreads)
 dct_kernel(const float* __restrict__ feat, const float* __restrict__ basis_t, const int64_t* __restrict__ frame_off,
            const int32_t* __restrict__ block_clip, int64_t total_frames, int M, int n_streams, int n_mfcc,
            float* __restrict__ out) {
-    extern __shared__ __align__(16) float s_basis[];       // [M][4 * NC4]
-    for (int i = threadIdx.x; i < M * 4 * NC4; i += kDctThreads) s_basis[i] = basis_t[i];
+    extern __shared__ __align__(16) float s_basis[];       // [M rounded up to kRows][4 * NC4], zero rows at the end
+    const int m_pad = (M + kRows - 1) / kRows * kRows;
+    for (int i = threadIdx.x; i < m_pad * 4 * NC4; i += kDctThreads) s_basis[i] = (i < M * 4 * NC4) ? basis_t[i] : 0.f;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t task = (int64_t)blockIdx.x * kDctWarps + warp;       // (frame block, stream)
-    const int64_t n_blocks = (total_frames + 31) / 32;
-    if (task >= n_blocks * n_streams) return;
-    const int stream = (int)(task % n_streams);
-    const int64_t gf = (task / n_streams) * 32 + lane;
-    if (gf >= total_frames) return;
-    const int c = find_clip_hint(frame_off, block_clip, gf);
-    const int64_t fo = __ldg(frame_off + c);
-    const int64_t T = __ldg(frame_off + c + 1) - fo;
-    const float* x = feat + (int64_t)(n_streams * M) * fo + (int64_t)(stream * M) * T + (gf - fo);
-    float* y = out + (int64_t)(n_streams * n_mfcc) * fo + (int64_t)(stream * n_mfcc) * T + (gf - fo);
-    float acc[4 * NC4];
-#pragma unroll
-    for (int k = 0; k < 4 * NC4; ++k) acc[k] = 0.f;
+    const int groups = n_streams / COLS;                                  // launch guarantees divisibility
+    const int64_t n_tasks = ((total_frames + 31) / 32) * groups;          // task = (32-frame block, stream group)
     const float4* b4 = reinterpret_cast<const float4*>(s_basis);
-#pragma unroll 8
-    for (int m = 0; m < M; ++m) {          // unrolled so that eight row loads are in flight per lane
-        const float v = __ldg(x + (int64_t)m * T);
+    // the basis is staged once per CTA, so every warp walks many tasks (grid-stride)
+    for (int64_t task = (int64_t)blockIdx.x * kDctWarps + warp; task < n_tasks; task += (int64_t)gridDim.x * kDctWarps) {
+        const int stream = (int)(task % groups) * COLS;
+        const int64_t gf = (task / groups) * 32 + lane;
+        if (gf >= total_frames) continue;
+        const int c = find_clip_hint(frame_off, block_clip, gf);
+        const int64_t fo = __ldg(frame_off + c);
+        const int64_t T = __ldg(frame_off + c + 1) - fo;
+        const float* x = feat + (int64_t)(n_streams * M) * fo + (int64_t)(stream * M) * T + (gf - fo);
+        float* y = out + (int64_t)(n_streams * n_mfcc) * fo + (int64_t)(stream * n_mfcc) * T + (gf - fo);
+        const int64_t xs = (int64_t)M * T, ys = (int64_t)n_mfcc * T;      // stream pitch of the input / output
+        float acc[COLS][4 * NC4];
 #pragma unroll
-        for (int k = 0; k < NC4; ++k) {
-            const float4 w = b4[m * NC4 + k];
-            acc[4 * k + 0] = fmaf(w.x, v, acc[4 * k + 0]);
-            acc[4 * k + 1] = fmaf(w.y, v, acc[4 * k + 1]);
-            acc[4 * k + 2] = fmaf(w.z, v, acc[4 * k + 2]);
-            acc[4 * k + 3] = fmaf(w.w, v, acc[4 * k + 3]);
+        for (int s = 0; s < COLS; ++s)
+#pragma unroll
+            for (int k = 0; k < 4 * NC4; ++k) acc[s][k] = 0.f;
+        // rows in batches of kRows; the next batch is requested before the current one is consumed, so that
+        // kRows..2*kRows row loads per lane and stream are in flight (the kernel is latency-bound otherwise)
+        float cur[COLS][kRows], nxt[COLS][kRows];
+#pragma unroll
+        for (int s = 0; s < COLS; ++s)
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) cur[s][u] = (u < M) ? __ldg(x + s * xs + (int64_t)u * T) : 0.f;
+#pragma unroll 1
+        for (int m0 = 0; m0 < M; m0 += kRows) {
+            const float* xn = x + (int64_t)(m0 + kRows) * T;
+#pragma unroll
+            for (int s = 0; s < COLS; ++s)
+#pragma unroll
+                for (int u = 0; u < kRows; ++u) nxt[s][u] = (m0 + kRows + u < M) ? __ldg(xn + s * xs + (int64_t)u * T) : 0.f;
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+#pragma unroll
+                for (int k = 0; k < NC4; ++k) {
+                    const float4 w = b4[(m0 + u) * NC4 + k];       // rows >= M of the staged basis are zero
+#pragma unroll
+                    for (int s = 0; s < COLS; ++s) {
+                        const float v = cur[s][u];
+                        acc[s][4 * k + 0] = fmaf(w.x, v, acc[s][4 * k + 0]);
+                        acc[s][4 * k + 1] = fmaf(w.y, v, acc[s][4 * k + 1]);
+                        acc[s][4 * k + 2] = fmaf(w.z, v, acc[s][4 * k + 2]);
+                        acc[s][4 * k + 3] = fmaf(w.w, v, acc[s][4 * k + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < COLS; ++s)
+#pragma unroll
+                for (int u = 0; u < kRows; ++u) cur[s][u] = nxt[s][u];
         }
-    }
 #pragma unroll
-    for (int k = 0; k < 4 * NC4; ++k)
-        if (k < n_mfcc) y[(int64_t)k * T] = acc[k];
+        for (int s = 0; s < COLS; ++s)
+#pragma unroll
+            for (int k = 0; k < 4 * NC4; ++k)
+                if (k < n_mfcc) y[s * ys + (int64_t)k * T] = acc[s][k];
+    }
 }
 
 }  // namespace
@@ -103,16 +137,20 @@ int launch_dct(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int M, int
             d_basis = it->second;
         }
     }
-    const size_t smem = sizeof(float) * (size_t)M * ncols;
+    const size_t smem = sizeof(float) * (size_t)((M + kRows - 1) / kRows * kRows) * ncols;
     if (smem > (size_t)ctx->max_smem_optin) {
         set_error("dct: basis of %zu bytes does not fit shared memory", smem);
         return HPSS_ERR_UNSUPPORTED;
     }
-    const int64_t n_tasks = ((total + 31) / 32) * n_streams;
-    const unsigned grid = (unsigned)((n_tasks + kDctWarps - 1) / kDctWarps);
+    // two streams per lane while the accumulators fit comfortably in registers (n_mfcc <= 24)
+    const int cols = (n_streams % 2 == 0 && nc4 <= 6) ? 2 : 1;
+    const int64_t n_tasks = ((total + 31) / 32) * (n_streams / cols);
+    const int64_t want = (n_tasks + kDctWarps - 1) / kDctWarps;
+    static const int mult = [] { const char* e = getenv("HPSS_DCT_GRID_MULT"); return e ? atoi(e) : 8; }();
+    const unsigned grid = (unsigned)(mult > 0 ? std::min<int64_t>(want, (int64_t)ctx->sm_count * mult) : want);
 #define HPSS_DCT_LAUNCH(NC4)                                                                                       \
     case NC4: {                                                                                                    \
-        auto kern = dct_kernel<NC4>;                                                                               \
+        auto kern = (cols == 2 && NC4 <= 6) ? dct_kernel<NC4, (NC4 <= 6 ? 2 : 1)> : dct_kernel<NC4, 1>;            \
         HPSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
         kern<<<grid, kDctThreads, smem, st>>>(feat, d_basis, b->d_frame_off, b->d_block_clip, total, M, n_streams, \
                                               n_mfcc, out);                                                        \
