@@ -125,9 +125,12 @@ int get_fft_plan(hpss_ctx* ctx, int n_fft, int win, FftPlan** out) {
         tf[k] = make_float2((float)cos(a), (float)sin(a));
     }
     HPSS_CUDA(cudaMalloc(&p->d_window, sizeof(float) * n_fft));
+    HPSS_CUDA(cudaMalloc(&p->d_window_half, sizeof(float) * n_fft));
     HPSS_CUDA(cudaMalloc(&p->d_tw_half, sizeof(float2) * p->n2));
     HPSS_CUDA(cudaMalloc(&p->d_tw_full, sizeof(float2) * (p->n2 + 1)));
     HPSS_CUDA(cudaMemcpy(p->d_window, w.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
+    for (auto& v : w) v *= 0.5f;       // exact; the specialised kernel keeps Z/2 so that the unpack needs no halving
+    HPSS_CUDA(cudaMemcpy(p->d_window_half, w.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
     HPSS_CUDA(cudaMemcpy(p->d_tw_half, th.data(), sizeof(float2) * p->n2, cudaMemcpyHostToDevice));
     HPSS_CUDA(cudaMemcpy(p->d_tw_full, tf.data(), sizeof(float2) * (p->n2 + 1), cudaMemcpyHostToDevice));
     ctx->fft_plans[key] = p;
@@ -495,7 +498,7 @@ int hpss_ctx_destroy(hpss_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto& kv : ctx->fft_plans) {
-        cudaFree(kv.second->d_window); cudaFree(kv.second->d_tw_half); cudaFree(kv.second->d_tw_full);
+        cudaFree(kv.second->d_window); cudaFree(kv.second->d_window_half); cudaFree(kv.second->d_tw_half); cudaFree(kv.second->d_tw_full);
         delete kv.second;
     }
     for (auto& kv : ctx->dct_plans) cudaFree(kv.second);

@@ -40,6 +40,7 @@ struct FftPlan {
     int n_pass = 0;
     int radix[kMaxRadixPasses] = {0};
     float* d_window = nullptr;   // n_fft floats (periodic Hann, centre padded)
+    float* d_window_half = nullptr;   // the same x 0.5 (stft_fast.cu)
     float2* d_tw_half = nullptr; // n2 entries exp(-2 pi i k / n2)
     float2* d_tw_full = nullptr; // n2+1 entries exp(-2 pi i k / n_fft)
 };

@@ -49,8 +49,12 @@ struct FastCfg {
     static constexpr int SEG = (TT - 1) * HOP + NFFT;                   // samples of a full tile
     static constexpr int SEGP = SEG + PAD * ((SEG + HOP - 1) / HOP);    // padded
     static constexpr int G = NT / 16;                                   // half-warp groups per CTA
+#ifndef HPSS_K1_GLOBAL_TABLES
+#define HPSS_K1_GLOBAL_TABLES 1     // 1: window / twiddles are read through L1 (__ldg), not staged per CTA
+#endif
+    static constexpr bool GT = HPSS_K1_GLOBAL_TABLES != 0;
     static constexpr size_t smem_bytes =
-        sizeof(float2) * ((size_t)TT * ZS + N2 + (N2 / 2 + 1)) + sizeof(float) * ((size_t)NFFT + SEGP + 4);
+        sizeof(float2) * ((size_t)TT * ZS + (GT ? 0 : N2 + (N2 / 2 + 1))) + sizeof(float) * ((size_t)(GT ? 0 : NFFT) + SEGP + 4);
     static_assert(NA * NB == N2, "N2 = NA * NB");
     static_assert(HOP % (2 * NB) == 0, "pad offsets must be compile-time constants");
     static_assert(HOP % 4 == 0 && NT % 32 == 0, "vector staging");
@@ -67,10 +71,14 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
     constexpr int N2 = C::N2, ZS = C::ZS, PAD = C::PAD, HOPP = C::HOPP, G = C::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* Z = reinterpret_cast<float2*>(smem_raw);            // [TT][ZS]
-    float2* s_twh = Z + (size_t)C::TT * ZS;                     // [N2]      exp(-2 pi i k / N2)
-    float2* s_twf = s_twh + N2;                                 // [N2/2+1]  exp(-2 pi i k / NFFT)
-    float* s_win = reinterpret_cast<float*>(s_twf + (N2 / 2 + 1));
-    float* s_samp = s_win + NFFT;                               // padded: sample s at s + PAD * (s / HOP)
+    float2* s_twh_ = Z + (size_t)C::TT * ZS;                    // [N2]      exp(-2 pi i k / N2)
+    float2* s_twf_ = s_twh_ + (C::GT ? 0 : N2);                 // [N2/2+1]  exp(-2 pi i k / NFFT)
+    float* s_win_ = reinterpret_cast<float*>(s_twf_ + (C::GT ? 0 : (N2 / 2 + 1)));
+    float* s_samp = s_win_ + (C::GT ? 0 : NFFT);                // padded: sample s at s + PAD * (s / HOP)
+    // tables: staged copies, or (GT) the L1-resident global arrays (the window is then pre-halved on the host)
+    const float2* s_twh = C::GT ? tw_half : s_twh_;
+    const float2* s_twf = C::GT ? tw_full : s_twf_;
+    const float* s_win = C::GT ? window : s_win_;
 
     const int tid = threadIdx.x;
     const int fr = tid & 15;
@@ -104,12 +112,14 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
 
     // ---- stage tables and the sample segment
     // window x 0.5 (exact): the spectrum buffer then holds Z/2 and the unpack needs no halving
-    for (int i = tid; i < NFFT / 2; i += NT) {
-        const float2 wv = __ldg(reinterpret_cast<const float2*>(window) + i);
-        reinterpret_cast<float2*>(s_win)[i] = make_float2(0.5f * wv.x, 0.5f * wv.y);
+    if (!C::GT) {
+        for (int i = tid; i < NFFT / 2; i += NT) {
+            const float2 wv = __ldg(reinterpret_cast<const float2*>(window) + i);
+            reinterpret_cast<float2*>(s_win_)[i] = make_float2(0.5f * wv.x, 0.5f * wv.y);
+        }
+        for (int i = tid; i < N2; i += NT) s_twh_[i] = __ldg(tw_half + i);
+        for (int i = tid; i <= N2 / 2; i += NT) s_twf_[i] = __ldg(tw_full + i);
     }
-    for (int i = tid; i < N2; i += NT) s_twh[i] = __ldg(tw_half + i);
-    for (int i = tid; i <= N2 / 2; i += NT) s_twf[i] = __ldg(tw_full + i);
     {
         if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
             const float4* src4 = reinterpret_cast<const float4*>(src);
@@ -138,7 +148,7 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
                 const int j0 = NB * q;                                   // compile-time after unrolling
                 const int po = (2 * j0 + PAD * ((2 * j0) / HOP)) / 2;    // float2 offset in the padded staging
                 const float2 xv = xs[po + b];
-                const float2 wv = ws[j0 + b];
+                const float2 wv = C::GT ? __ldg(ws + j0 + b) : ws[j0 + b];
                 v[q] = make_float2(xv.x * wv.x, xv.y * wv.y);
             }
             Dft<NA>::run(v);
@@ -159,7 +169,7 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
 #pragma unroll
             for (int b = 1; b < NB; ++b) {
                 const float2 a = z[NA * b];
-                const float2 w = s_twh[b * k1];
+                const float2 w = C::GT ? __ldg(s_twh + b * k1) : s_twh[b * k1];
                 v[b] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
             }
             Dft<NB>::run(v);
@@ -182,7 +192,7 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
             const float2 zc = zrow[N2 - k];
             const float2 e = make_float2(zk.x + zc.x, zk.y - zc.y);
             const float2 o = make_float2(zk.y + zc.y, zc.x - zk.x);
-            const float2 w = s_twf[k];
+            const float2 w = C::GT ? __ldg(s_twf + k) : s_twf[k];
             const float2 wo = make_float2(w.x * o.x - w.y * o.y, w.x * o.y + w.y * o.x);
             xa = make_float2(e.x + wo.x, e.y + wo.y);
             xb = make_float2(e.x - wo.x, wo.y - e.y);
@@ -240,7 +250,7 @@ int launch_cfg(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* p
         uni.n_clips = b->n_clips;
         uni.total_samples = b->sample_off[b->n_clips];
         const int64_t n_tiles = ((int64_t)b->n_clips * uni.fpc + C::TT - 1) / C::TT;
-        kern<<<(unsigned)n_tiles, NT, C::smem_bytes, st>>>(wave, b->d_sample_off, b->d_frame_off, nullptr, plan->d_window,
+        kern<<<(unsigned)n_tiles, NT, C::smem_bytes, st>>>(wave, b->d_sample_off, b->d_frame_off, nullptr, (C::GT ? plan->d_window_half : plan->d_window),
                                                            plan->d_tw_half, plan->d_tw_full, power, S,
                                                            reinterpret_cast<float2*>(cplx), uni);
     } else {
@@ -254,7 +264,7 @@ int launch_cfg(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* p
         if (rc) return rc;
         if (b->n_stft_tiles == 0) return HPSS_OK;
         kern<<<b->n_stft_tiles, NT, C::smem_bytes, st>>>(wave, b->d_sample_off, b->d_frame_off, b->d_stft_tiles,
-                                                         plan->d_window, plan->d_tw_half, plan->d_tw_full, power, S,
+                                                         (C::GT ? plan->d_window_half : plan->d_window), plan->d_tw_half, plan->d_tw_full, power, S,
                                                          reinterpret_cast<float2*>(cplx), uni);
     }
     HPSS_LAUNCHED("stft_fast_kernel");
