@@ -92,9 +92,9 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
         src = wave + v0 * HOP;
         const int64_t left = uni.total_samples - v0 * HOP;
         seg = (int)(left < (int64_t)C::SEG ? left : (int64_t)C::SEG);
-        const int64_t v = v0 + fr;
-        const int c = (int)(v / uni.fpc);
-        const int t = (int)(v - (int64_t)c * uni.fpc);
+        const uint32_t v = (uint32_t)v0 + fr;              // virtual frames fit 32 bits (checked at launch)
+        const int c = (int)(v / (uint32_t)uni.fpc);
+        const int t = (int)(v - (uint32_t)c * (uint32_t)uni.fpc);
         T = uni.T;
         live = c < uni.n_clips && t < T;
         base = (int64_t)(N2 + 1) * ((int64_t)c * T) + t;
@@ -198,8 +198,10 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
             xb = make_float2(e.x - wo.x, wo.y - e.y);
         };
         if (MODE == 0) {                                   // magnitudes only (the feature path)
-#pragma unroll 2
-            for (int k = g; k < N2 / 2; k += G) {
+            static_assert((N2 / 2) % G == 0, "every group unpacks the same number of bin pairs");
+#pragma unroll
+            for (int i = 0; i < (N2 / 2) / G; ++i) {       // fully unrolled: table and buffer offsets become immediates
+                const int k = g + i * G;
                 float2 xa, xb;
                 pair(k, xa, xb);
                 *reinterpret_cast<float*>(Sg + (int64_t)k * T4) = fast_sqrt(xa.x * xa.x + xa.y * xa.y);
@@ -243,7 +245,7 @@ int launch_cfg(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* p
     HPSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
     UniformBatch uni{0, 0, 0, 0};
     const int64_t L = b->uniform_samples;
-    if (L > 0 && L % HOP == 0 && b->uniform_frames > 0 && L / HOP < 0x7fffffff && !getenv("HPSS_NO_UNIFORM_STFT")) {
+    if (L > 0 && L % HOP == 0 && b->uniform_frames > 0 && (int64_t)b->n_clips * (L / HOP) + C::TT < 0x7fffffff && !getenv("HPSS_NO_UNIFORM_STFT")) {
         // equal clips, length a multiple of the hop: 16 consecutive virtual frames per tile, across clip borders
         uni.fpc = (int)(L / HOP);
         uni.T = (int)b->uniform_frames;

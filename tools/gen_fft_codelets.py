@@ -4,7 +4,9 @@
 A codelet `dftN(float2 (&v)[N])` transforms v in place (natural order in, natural order out,
 forward transform exp(-2 pi i jk / N)).  Sizes are built by Cooley-Tukey recursion down to hand-written
 radix-2/3/4/5 butterflies; every twiddle is a literal constant, quarter turns cost nothing.  The op list is
-evaluated with numpy against numpy.fft before anything is written.
+evaluated with numpy against numpy.fft before anything is written.  Coprime splits (10 = 2 x 5, 20 = 4 x 5) use the
+Good-Thomas prime-factor map, which needs no twiddles between the stages (DFT-10: 140 -> 92 operations, DFT-20:
+344 -> 224).
 
 Usage:  python tools/gen_fft_codelets.py [--out PATH] [--sizes 10,20,16,32]
 """
@@ -123,6 +125,20 @@ def split(n):
     raise ValueError(f"cannot factor {n} into 2/3/4/5")
 
 
+def dft_pfa(P, v, n1, n2):
+    """Good-Thomas prime-factor step for coprime n1, n2: no twiddles between the two stages.
+    Input map n = (n2*j1 + n1*j2) mod N, output map (CRT) k = (k1*n2*(n2^-1 mod n1) + k2*n1*(n1^-1 mod n2)) mod N."""
+    n = n1 * n2
+    A = [dft(P, [v[(n2 * j1 + n1 * j2) % n] for j1 in range(n1)]) for j2 in range(n2)]      # A[j2][k1]
+    e1, e2 = n2 * pow(n2, -1, n1), n1 * pow(n1, -1, n2)
+    out = [None] * n
+    for k1 in range(n1):
+        res = dft(P, [A[j2][k1] for j2 in range(n2)])
+        for k2 in range(n2):
+            out[(k1 * e1 + k2 * e2) % n] = res[k2]
+    return out
+
+
 def dft(P, v):
     n = len(v)
     if n == 1:
@@ -130,6 +146,8 @@ def dft(P, v):
     if n in BASE:
         return BASE[n](P, v)
     n1, n2 = split(n)            # x[n2*j1 + j2]; X[k1 + n1*k2]
+    if math.gcd(n1, n2) == 1:
+        return dft_pfa(P, v, n1, n2)
     A = [dft(P, [v[n2 * j1 + j2] for j1 in range(n1)]) for j2 in range(n2)]
     out = [None] * n
     for k1 in range(n1):
