@@ -133,6 +133,21 @@ int get_fft_plan(hpss_ctx* ctx, int n_fft, int win, FftPlan** out) {
     HPSS_CUDA(cudaMemcpy(p->d_window_half, w.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
     HPSS_CUDA(cudaMemcpy(p->d_tw_half, th.data(), sizeof(float2) * p->n2, cudaMemcpyHostToDevice));
     HPSS_CUDA(cudaMemcpy(p->d_tw_full, tf.data(), sizeof(float2) * (p->n2 + 1), cudaMemcpyHostToDevice));
+    int na = 0, nb = 0;
+    if (stft_fast_split(n_fft, &na, &nb)) {
+        std::vector<float2> wbq((size_t)p->n2), tkb((size_t)p->n2);
+        for (int b = 0; b < nb; ++b)
+            for (int q = 0; q < na; ++q) {
+                const int n = nb * q + b;
+                wbq[(size_t)b * na + q] = make_float2(w[2 * n], w[2 * n + 1]);         // w is already halved here
+            }
+        for (int k1 = 0; k1 < na; ++k1)
+            for (int b = 0; b < nb; ++b) tkb[(size_t)k1 * nb + b] = th[(b * k1) % p->n2];
+        HPSS_CUDA(cudaMalloc(&p->d_win_bq, sizeof(float2) * p->n2));
+        HPSS_CUDA(cudaMalloc(&p->d_tw_kb, sizeof(float2) * p->n2));
+        HPSS_CUDA(cudaMemcpy(p->d_win_bq, wbq.data(), sizeof(float2) * p->n2, cudaMemcpyHostToDevice));
+        HPSS_CUDA(cudaMemcpy(p->d_tw_kb, tkb.data(), sizeof(float2) * p->n2, cudaMemcpyHostToDevice));
+    }
     ctx->fft_plans[key] = p;
     *out = p;
     return HPSS_OK;
@@ -498,7 +513,7 @@ int hpss_ctx_destroy(hpss_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto& kv : ctx->fft_plans) {
-        cudaFree(kv.second->d_window); cudaFree(kv.second->d_window_half); cudaFree(kv.second->d_tw_half); cudaFree(kv.second->d_tw_full);
+        cudaFree(kv.second->d_window); cudaFree(kv.second->d_window_half); cudaFree(kv.second->d_win_bq); cudaFree(kv.second->d_tw_kb); cudaFree(kv.second->d_tw_half); cudaFree(kv.second->d_tw_full);
         delete kv.second;
     }
     for (auto& kv : ctx->dct_plans) cudaFree(kv.second);

@@ -43,6 +43,10 @@ struct FftPlan {
     float* d_window_half = nullptr;   // the same x 0.5 (stft_fast.cu)
     float2* d_tw_half = nullptr; // n2 entries exp(-2 pi i k / n2)
     float2* d_tw_full = nullptr; // n2+1 entries exp(-2 pi i k / n_fft)
+    // stft_fast.cu (n2 = NA x NB): tables laid out in the order the two passes read them, so that one 16-byte
+    // load fetches two entries:  win_bq[b*NA + q] = 0.5 * (w[2n], w[2n+1]), n = NB*q + b;  tw_kb[k1*NB + b] = W_n2^(b*k1)
+    float2* d_win_bq = nullptr;
+    float2* d_tw_kb = nullptr;
 };
 
 struct MelPlan {
@@ -111,6 +115,7 @@ struct hpss_batch {
 namespace hpss {
 
 int get_fft_plan(hpss_ctx* ctx, int n_fft, int win, FftPlan** out);
+bool stft_fast_split(int n_fft, int* na, int* nb);      // the NA x NB split of the specialised kernel, if any
 int get_mel_plan(hpss_ctx* ctx, int sr, int n_fft, int n_mels, MelPlan** out);
 int ensure_workspace(hpss_ctx* ctx, size_t bytes);
 int ensure_stft_tiles(hpss_batch* b, int tt);

@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(NT)
 stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sample_off,
                  const int64_t* __restrict__ frame_off, const int2* __restrict__ tiles,
                  const float* __restrict__ window, const float2* __restrict__ tw_half,
-                 const float2* __restrict__ tw_full, int power, float* __restrict__ S, float2* __restrict__ cplx,
+                 const float2* __restrict__ tw_full, const float2* __restrict__ win_bq,
+                 const float2* __restrict__ tw_kb, int power, float* __restrict__ S, float2* __restrict__ cplx,
                  UniformBatch uni) {
     using C = FastCfg<NFFT, HOP, NA, NB, NT>;
     constexpr int N2 = C::N2, ZS = C::ZS, PAD = C::PAD, HOPP = C::HOPP, G = C::G;
@@ -121,14 +122,13 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
         for (int i = tid; i <= N2 / 2; i += NT) s_twf_[i] = __ldg(tw_full + i);
     }
     {
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-            const float4* src4 = reinterpret_cast<const float4*>(src);
-            for (int i = tid; i < seg / 4; i += NT) {
-                const float4 v = __ldg(src4 + i);
-                const int s = 4 * i;
-                float2* d = reinterpret_cast<float2*>(s_samp + s + PAD * (s / HOP));
-                d[0] = make_float2(v.x, v.y);
-                d[1] = make_float2(v.z, v.w);
+        // 8-byte granularity: consecutive lanes write consecutive float2 (no bank conflicts; the padded layout
+        // keeps 8-byte but not 16-byte alignment)
+        if ((reinterpret_cast<uintptr_t>(src) & 7) == 0 && (seg & 1) == 0) {
+            const float2* src2 = reinterpret_cast<const float2*>(src);
+            for (int i = tid; i < seg / 2; i += NT) {
+                const int s = 2 * i;
+                *reinterpret_cast<float2*>(s_samp + s + PAD * (s / HOP)) = __ldg(src2 + i);
             }
         } else {
             for (int s = tid; s < seg; s += NT) s_samp[s + PAD * (s / HOP)] = __ldg(src + s);
@@ -143,12 +143,20 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
 #pragma unroll 1
         for (int b = g; b < NB; b += G) {
             float2 v[NA];
+            const float4* wq = reinterpret_cast<const float4*>(win_bq + b * NA);     // two q per 16-byte load
 #pragma unroll
             for (int q = 0; q < NA; ++q) {
                 const int j0 = NB * q;                                   // compile-time after unrolling
                 const int po = (2 * j0 + PAD * ((2 * j0) / HOP)) / 2;    // float2 offset in the padded staging
                 const float2 xv = xs[po + b];
-                const float2 wv = C::GT ? __ldg(ws + j0 + b) : ws[j0 + b];
+                float2 wv;
+                if (C::GT) {
+                    static_assert(NA % 2 == 0, "window pairs");
+                    const float4 w2 = __ldg(wq + q / 2);                 // CSE'd between q and q + 1
+                    wv = (q & 1) ? make_float2(w2.z, w2.w) : make_float2(w2.x, w2.y);
+                } else {
+                    wv = ws[j0 + b];
+                }
                 v[q] = make_float2(xv.x * wv.x, xv.y * wv.y);
             }
             Dft<NA>::run(v);
@@ -166,10 +174,18 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
             float2 v[NB];
             float2* z = Z + fr * ZS + k1;
             v[0] = z[0];
+            const float4* tq = reinterpret_cast<const float4*>(tw_kb + k1 * NB);     // two b per 16-byte load
 #pragma unroll
             for (int b = 1; b < NB; ++b) {
                 const float2 a = z[NA * b];
-                const float2 w = C::GT ? __ldg(s_twh + b * k1) : s_twh[b * k1];
+                float2 w;
+                if (C::GT) {
+                    static_assert(NB % 2 == 0, "twiddle pairs");
+                    const float4 w2 = __ldg(tq + b / 2);
+                    w = (b & 1) ? make_float2(w2.z, w2.w) : make_float2(w2.x, w2.y);
+                } else {
+                    w = s_twh[b * k1];
+                }
                 v[b] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
             }
             Dft<NB>::run(v);
@@ -253,7 +269,7 @@ int launch_cfg(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* p
         uni.total_samples = b->sample_off[b->n_clips];
         const int64_t n_tiles = ((int64_t)b->n_clips * uni.fpc + C::TT - 1) / C::TT;
         kern<<<(unsigned)n_tiles, NT, C::smem_bytes, st>>>(wave, b->d_sample_off, b->d_frame_off, nullptr, (C::GT ? plan->d_window_half : plan->d_window),
-                                                           plan->d_tw_half, plan->d_tw_full, power, S,
+                                                           plan->d_tw_half, plan->d_tw_full, plan->d_win_bq, plan->d_tw_kb, power, S,
                                                            reinterpret_cast<float2*>(cplx), uni);
     } else {
         // tile height: at most 16 frames, an even split of the longest clip
@@ -266,7 +282,7 @@ int launch_cfg(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* p
         if (rc) return rc;
         if (b->n_stft_tiles == 0) return HPSS_OK;
         kern<<<b->n_stft_tiles, NT, C::smem_bytes, st>>>(wave, b->d_sample_off, b->d_frame_off, b->d_stft_tiles,
-                                                         (C::GT ? plan->d_window_half : plan->d_window), plan->d_tw_half, plan->d_tw_full, power, S,
+                                                         (C::GT ? plan->d_window_half : plan->d_window), plan->d_tw_half, plan->d_tw_full, plan->d_win_bq, plan->d_tw_kb, power, S,
                                                          reinterpret_cast<float2*>(cplx), uni);
     }
     HPSS_LAUNCHED("stft_fast_kernel");
@@ -274,6 +290,16 @@ int launch_cfg(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* p
 }
 
 }  // namespace
+
+bool stft_fast_split(int n_fft, int* na, int* nb) {
+    switch (n_fft) {
+        case 400: *na = 10; *nb = 20; return true;
+        case 512: *na = 16; *nb = 16; return true;
+        case 1024: *na = 16; *nb = 32; return true;
+        case 2048: *na = 32; *nb = 32; return true;
+        default: return false;
+    }
+}
 
 // *handled = false (nothing launched) when (n_fft, hop) has no specialisation; the caller then runs the
 // generic mixed-radix kernel.
