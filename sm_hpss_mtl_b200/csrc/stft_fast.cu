@@ -42,13 +42,16 @@ struct UniformBatch {
 template <int NFFT, int HOP, int NA, int NB, int NT>
 struct FastCfg {
     static constexpr int N2 = NFFT / 2;
-    static constexpr int TT = 16;
+#ifndef HPSS_K1_TT400
+#define HPSS_K1_TT400 16            // frames per tile of the 400/160 configuration (16 or 32; 32 measured 5 % slower)
+#endif
+    static constexpr int TT = (NFFT == 400) ? HPSS_K1_TT400 : 16;       // frames per tile = lanes per group
     static constexpr int ZS = N2 | 1;                                   // float2 stride between frames
     static constexpr int PAD = ((HOP / 2) % 2 == 0) ? 2 : 0;            // (HOP + PAD) / 2 odd
     static constexpr int HOPP = HOP + PAD;
     static constexpr int SEG = (TT - 1) * HOP + NFFT;                   // samples of a full tile
     static constexpr int SEGP = SEG + PAD * ((SEG + HOP - 1) / HOP);    // padded
-    static constexpr int G = NT / 16;                                   // half-warp groups per CTA
+    static constexpr int G = NT / TT;                                   // lane groups (one frame per lane) per CTA
 #ifndef HPSS_K1_GLOBAL_TABLES
 #define HPSS_K1_GLOBAL_TABLES 1     // 1: window / twiddles are read through L1 (__ldg), not staged per CTA
 #endif
@@ -82,8 +85,8 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
     const float* s_win = C::GT ? window : s_win_;
 
     const int tid = threadIdx.x;
-    const int fr = tid & 15;
-    const int g = tid >> 4;
+    const int fr = tid % C::TT;
+    const int g = tid / C::TT;
     int T, seg;
     int64_t base;                  // element offset of (bin 0, this lane's frame) in S
     bool live;
@@ -307,7 +310,7 @@ int launch_stft_fast(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftP
                      float* cplx, cudaStream_t st, bool* handled) {
     *handled = true;
     const int n = plan->n_fft;
-    if (n == 400 && hop == 160) return launch_cfg<400, 160, 10, 20, 160>(ctx, b, wave, plan, power, S, cplx, st);
+    if (n == 400 && hop == 160) return launch_cfg<400, 160, 10, 20, 10 * HPSS_K1_TT400>(ctx, b, wave, plan, power, S, cplx, st);
     if (n == 512 && hop == 160) return launch_cfg<512, 160, 16, 16, 256>(ctx, b, wave, plan, power, S, cplx, st);
     if (n == 512 && hop == 128) return launch_cfg<512, 128, 16, 16, 256>(ctx, b, wave, plan, power, S, cplx, st);
     if (n == 1024 && hop == 256) return launch_cfg<1024, 256, 16, 32, 256>(ctx, b, wave, plan, power, S, cplx, st);
