@@ -28,6 +28,10 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: NCCL's version / debug banner (printed to stdout when NCCL_DEBUG is set in the
+# environment) goes to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 

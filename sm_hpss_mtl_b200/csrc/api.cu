@@ -148,6 +148,18 @@ int get_fft_plan(hpss_ctx* ctx, int n_fft, int win, FftPlan** out) {
         HPSS_CUDA(cudaMemcpy(p->d_win_bq, wbq.data(), sizeof(float2) * p->n2, cudaMemcpyHostToDevice));
         HPSS_CUDA(cudaMemcpy(p->d_tw_kb, tkb.data(), sizeof(float2) * p->n2, cudaMemcpyHostToDevice));
     }
+    if (n_fft == 400) {
+        std::vector<float> wr(400);
+        std::vector<float2> tr(11 * 20);
+        for (int b = 0; b < 20; ++b)
+            for (int q = 0; q < 20; ++q) wr[b * 20 + q] = 2.0f * w[20 * q + b];       // w was halved above (exactly)
+        for (int k1 = 0; k1 <= 10; ++k1)
+            for (int b = 0; b < 20; ++b) tr[k1 * 20 + b] = tf[b * k1];
+        HPSS_CUDA(cudaMalloc(&p->d_win_r400, sizeof(float) * wr.size()));
+        HPSS_CUDA(cudaMalloc(&p->d_tw_r400, sizeof(float2) * tr.size()));
+        HPSS_CUDA(cudaMemcpy(p->d_win_r400, wr.data(), sizeof(float) * wr.size(), cudaMemcpyHostToDevice));
+        HPSS_CUDA(cudaMemcpy(p->d_tw_r400, tr.data(), sizeof(float2) * tr.size(), cudaMemcpyHostToDevice));
+    }
     ctx->fft_plans[key] = p;
     *out = p;
     return HPSS_OK;
@@ -513,7 +525,7 @@ int hpss_ctx_destroy(hpss_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto& kv : ctx->fft_plans) {
-        cudaFree(kv.second->d_window); cudaFree(kv.second->d_window_half); cudaFree(kv.second->d_win_bq); cudaFree(kv.second->d_tw_kb); cudaFree(kv.second->d_tw_half); cudaFree(kv.second->d_tw_full);
+        cudaFree(kv.second->d_window); cudaFree(kv.second->d_window_half); cudaFree(kv.second->d_win_bq); cudaFree(kv.second->d_win_r400); cudaFree(kv.second->d_tw_r400); cudaFree(kv.second->d_tw_kb); cudaFree(kv.second->d_tw_half); cudaFree(kv.second->d_tw_full);
         delete kv.second;
     }
     for (auto& kv : ctx->dct_plans) cudaFree(kv.second);

@@ -47,6 +47,9 @@ struct FftPlan {
     // load fetches two entries:  win_bq[b*NA + q] = 0.5 * (w[2n], w[2n+1]), n = NB*q + b;  tw_kb[k1*NB + b] = W_n2^(b*k1)
     float2* d_win_bq = nullptr;
     float2* d_tw_kb = nullptr;
+    // stft_r400_kernel: win_r400[b*20 + q] = w[20q + b];  tw_r400[k1*20 + b] = W_400^(b*k1), k1 = 0..10
+    float* d_win_r400 = nullptr;
+    float2* d_tw_r400 = nullptr;
 };
 
 struct MelPlan {

@@ -251,6 +251,167 @@ stft_fast_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
     }
 }
 
+
+// ---- n_fft = 400, hop = 160, magnitudes only: real-input 20 x 20 split without an unpack step.
+// X[k1 + 20 k2] = sum_b ( W_400^(b k1) * Y[b][k1] ) W_20^(b k2),  Y[b][k1] = sum_q w[n] x[n] W_20^(q k1), n = 20 q + b.
+// Pass 1: twenty real-input DFT-20 codelets per frame (11 non-redundant outputs each; Y[b][0] and Y[b][10] are real
+// and share one float2 slot).  Pass 2: for k1 = 0..10 the twiddles and a complex DFT-20 whose outputs are final bins
+// (k <= 200) or mirrors of final bins (|X[400 - k]| = |X[k]|), so the magnitudes go from registers to global memory:
+// 440 instead of 800 complex values per frame pass through shared memory, one barrier and the unpack loop are gone.
+constexpr int kR400Threads = 192;         // 12 half-warp groups: 20 b over 12 groups in pass 1, 11 k1 in pass 2
+
+__global__ void __launch_bounds__(kR400Threads)
+stft_r400_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sample_off,
+                 const int64_t* __restrict__ frame_off, const int2* __restrict__ tiles,
+                 const float* __restrict__ win_rq, const float2* __restrict__ tw_r, float* __restrict__ S,
+                 UniformBatch uni) {
+    using C = FastCfg<400, 160, 10, 20, kR400Threads>;
+    constexpr int NFFT = 400, HOP = 160, NT = kR400Threads, ZS = 201, PAD = C::PAD, HOPP = C::HOPP, G = NT / 16;
+    static_assert(C::TT == 16 && PAD == 2, "layout");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Z = reinterpret_cast<float2*>(smem_raw);            // [16][ZS]: slot k1 (0..9) x 20 b; slot 0 = (Y[b][0], Y[b][10])
+    float* s_samp = reinterpret_cast<float*>(Z + (size_t)16 * ZS);
+
+    const int tid = threadIdx.x;
+    const int fr = tid & 15;
+    const int g = tid >> 4;
+    int T, seg;
+    int64_t base;
+    bool live;
+    const float* src;
+    if (uni.fpc > 0) {
+        const int64_t v0 = (int64_t)blockIdx.x * 16;
+        src = wave + v0 * HOP;
+        const int64_t left = uni.total_samples - v0 * HOP;
+        seg = (int)(left < (int64_t)C::SEG ? left : (int64_t)C::SEG);
+        const uint32_t v = (uint32_t)v0 + fr;
+        const int c = (int)(v / (uint32_t)uni.fpc);
+        const int t = (int)(v - (uint32_t)c * (uint32_t)uni.fpc);
+        T = uni.T;
+        live = c < uni.n_clips && t < T;
+        base = (int64_t)201 * ((int64_t)c * T) + t;
+    } else {
+        const int2 tile = tiles[blockIdx.x];
+        const int c = tile.x, t0 = tile.y;
+        const int64_t fo = frame_off[c];
+        T = (int)(frame_off[c + 1] - fo);
+        const int nf = min(16, T - t0);
+        src = wave + sample_off[c] + (int64_t)t0 * HOP;
+        seg = (nf - 1) * HOP + NFFT;
+        live = fr < nf;
+        base = (int64_t)201 * fo + t0 + fr;
+    }
+    if ((reinterpret_cast<uintptr_t>(src) & 7) == 0 && (seg & 1) == 0) {
+        // 160 threads stage two hop rows (2 x 80 float2) per step: no division, all loads issued before the stores
+        if (tid < 160) {
+            constexpr int STEPS = (C::SEG / HOP + 2) / 2;                 // 9 steps cover rows 0 .. 17
+            const int row0 = tid >= 80 ? 1 : 0, col = tid - 80 * row0;
+            const float2* sp = reinterpret_cast<const float2*>(src) + row0 * 80 + col;
+            float* dp = s_samp + row0 * HOPP + 2 * col;
+            const int lim = seg / 2 - (row0 * 80 + col);                  // float2 units left from this thread's start
+            float2 v[STEPS];
+#pragma unroll
+            for (int j = 0; j < STEPS; ++j) v[j] = (160 * j < lim) ? __ldg(sp + 160 * j) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < STEPS; ++j)
+                if (160 * j < lim) *reinterpret_cast<float2*>(dp + 2 * HOPP * j) = v[j];
+        }
+    } else {
+        for (int s = tid; s < seg; s += NT) s_samp[s + PAD * (s / HOP)] = __ldg(src + s);
+    }
+    __syncthreads();
+
+    // ---- pass 1: real-input DFT-20 over q of w[n] x[n], n = 20 q + b
+    if (live) {
+        const float* xs = s_samp + fr * HOPP;
+        float2* z = Z + fr * ZS;
+#pragma unroll 1
+        for (int b = g; b < 20; b += G) {
+            const float4* wq = reinterpret_cast<const float4*>(win_rq + b * 20);
+            float x[20];
+#pragma unroll
+            for (int q4 = 0; q4 < 5; ++q4) {
+                const float4 w4 = __ldg(wq + q4);
+                // n = 20 q + b < 160 for q < 8, < 320 for q < 16 (b < 20): the pad offset is a compile-time constant
+                x[4 * q4 + 0] = xs[20 * (4 * q4 + 0) + PAD * ((4 * q4 + 0) / 8) + b] * w4.x;
+                x[4 * q4 + 1] = xs[20 * (4 * q4 + 1) + PAD * ((4 * q4 + 1) / 8) + b] * w4.y;
+                x[4 * q4 + 2] = xs[20 * (4 * q4 + 2) + PAD * ((4 * q4 + 2) / 8) + b] * w4.z;
+                x[4 * q4 + 3] = xs[20 * (4 * q4 + 3) + PAD * ((4 * q4 + 3) / 8) + b] * w4.w;
+            }
+            float2 y[11];
+            rdft20(x, y);
+            z[b] = make_float2(y[0].x, y[10].x);
+#pragma unroll
+            for (int k1 = 1; k1 < 10; ++k1) z[20 * k1 + b] = y[k1];
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 2: twiddle W_400^(b k1), DFT-20 over b, |.| straight to global memory
+    if (live && g <= 10) {
+        const int k1 = g;
+        const bool first = k1 == 0, last = k1 == 10;
+        const float2* zp = Z + fr * ZS + (last ? 0 : 20 * k1);
+        const float4* tq = reinterpret_cast<const float4*>(tw_r + k1 * 20);
+        float2 v[20];
+#pragma unroll
+        for (int b2 = 0; b2 < 10; ++b2) {
+            const float4 w4 = __ldg(tq + b2);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int b = 2 * b2 + h;
+                const float2 a = zp[b];
+                const float re = last ? a.y : a.x;
+                const float im = (first || last) ? 0.f : a.y;
+                const float wx = h ? w4.z : w4.x, wy = h ? w4.w : w4.y;
+                v[b] = (b == 0) ? make_float2(re, im) : make_float2(re * wx - im * wy, re * wy + im * wx);
+            }
+        }
+        Dft<20>::run(v);
+        char* Sg = reinterpret_cast<char*>(S + base);
+        const int T4 = 4 * T;
+        const int kmax = first ? 10 : (last ? 9 : 19);          // the other outputs of k1 = 0, 10 repeat rows already covered
+#pragma unroll
+        for (int k2 = 0; k2 < 20; ++k2) {
+            const int row = (k2 < 10) ? k1 + 20 * k2 : 20 * (20 - k2) - k1;      // bin, or its mirror 400 - bin
+            if (k2 <= kmax)
+                *reinterpret_cast<float*>(Sg + (int64_t)row * T4) = fast_sqrt(v[k2].x * v[k2].x + v[k2].y * v[k2].y);
+        }
+    }
+}
+
+int launch_r400(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* plan, float* S, cudaStream_t st) {
+    using C = FastCfg<400, 160, 10, 20, kR400Threads>;
+    constexpr size_t smem = sizeof(float2) * 16 * 201 + sizeof(float) * (C::SEGP + 4);
+    HPSS_CUDA(cudaFuncSetAttribute(stft_r400_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    UniformBatch uni{0, 0, 0, 0};
+    const int64_t L = b->uniform_samples;
+    if (L > 0 && L % 160 == 0 && b->uniform_frames > 0 && (int64_t)b->n_clips * (L / 160) + 16 < 0x7fffffff &&
+        !getenv("HPSS_NO_UNIFORM_STFT")) {
+        uni.fpc = (int)(L / 160);
+        uni.T = (int)b->uniform_frames;
+        uni.n_clips = b->n_clips;
+        uni.total_samples = b->sample_off[b->n_clips];
+        const int64_t n_tiles = ((int64_t)b->n_clips * uni.fpc + 15) / 16;
+        stft_r400_kernel<<<(unsigned)n_tiles, kR400Threads, smem, st>>>(wave, b->d_sample_off, b->d_frame_off, nullptr,
+                                                                        plan->d_win_r400, plan->d_tw_r400, S, uni);
+    } else {
+        int tt = 16;
+        if (b->max_frames > 0) {
+            const int64_t nt = (b->max_frames + tt - 1) / tt;
+            tt = (int)((b->max_frames + nt - 1) / nt);
+        }
+        int rc = ensure_stft_tiles(b, tt);
+        if (rc) return rc;
+        if (b->n_stft_tiles == 0) return HPSS_OK;
+        stft_r400_kernel<<<b->n_stft_tiles, kR400Threads, smem, st>>>(wave, b->d_sample_off, b->d_frame_off,
+                                                                      b->d_stft_tiles, plan->d_win_r400,
+                                                                      plan->d_tw_r400, S, uni);
+    }
+    HPSS_LAUNCHED("stft_r400_kernel");
+    return HPSS_OK;
+}
+
 template <int NFFT, int HOP, int NA, int NB, int NT>
 int launch_cfg(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* plan, int power, float* S, float* cplx,
                cudaStream_t st) {
@@ -310,6 +471,8 @@ int launch_stft_fast(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftP
                      float* cplx, cudaStream_t st, bool* handled) {
     *handled = true;
     const int n = plan->n_fft;
+    static const bool use_r400 = [] { const char* e = getenv("HPSS_K1_REAL"); return !e || atoi(e) != 0; }();
+    if (n == 400 && hop == 160 && !power && !cplx && use_r400 && plan->d_win_r400) return launch_r400(ctx, b, wave, plan, S, st);
     if (n == 400 && hop == 160) return launch_cfg<400, 160, 10, 20, 10 * HPSS_K1_TT400>(ctx, b, wave, plan, power, S, cplx, st);
     if (n == 512 && hop == 160) return launch_cfg<512, 160, 16, 16, 256>(ctx, b, wave, plan, power, S, cplx, st);
     if (n == 512 && hop == 128) return launch_cfg<512, 128, 16, 16, 256>(ctx, b, wave, plan, power, S, cplx, st);

@@ -80,7 +80,7 @@ def test_median_all_fast_kernel_sizes(ctx):
 # ------------------------------------------------------------------------------ STFT
 STFT_CASES = [
     # (n_fft, win, hop, [L...])
-    (400, 400, 160, [16000]), (400, 400, 160, [16000, 400, 559, 560, 3000]),
+    (400, 400, 160, [16000]), (400, 400, 160, [16000, 400, 559, 560, 3000]), (400, 320, 160, [4001, 1234, 877]),
     (512, 400, 160, [16000, 8000]), (512, 512, 128, [9000]), (1024, 1024, 256, [20000]),
     (2048, 2048, 512, [40000]), (240, 200, 80, [5000]), (600, 600, 150, [7000]),
     # batches of equal clips whose length is a multiple of the hop: tiles of 16 virtual frames across clip borders
@@ -104,6 +104,15 @@ def test_stft_matches_oracle(ctx, n_fft, win, hop, Ls):
         e_c, e_m = rel_l2(got_c, want), rel_l2(got_m, np.abs(want))
         maxabs = float(np.abs(got_m - np.abs(want)).max())
         assert e_c < 1e-5 and e_m < 1e-5, f"rel-L2 complex {e_c:.2e} mag {e_m:.2e} max-abs {maxabs:.2e}"
+    # the magnitudes-only call (the feature path; for 400/160 a different kernel: real-input 20 x 20 split)
+    S0 = engine.stft_mag(batch, to_dev(np.concatenate(waves)), n_fft, win, hop)
+    torch.cuda.synchronize()
+    for c, y in enumerate(waves):
+        want = np.abs(lr.stft(y, n_fft=n_fft, hop_length=hop, win_length=win))
+        got = batch.clip(S0, F, c).cpu().numpy()
+        assert got.shape == want.shape
+        e = rel_l2(got, want)
+        assert e < 1e-5, f"magnitude-only path, clip {c}: rel-L2 {e:.2e} max-abs {float(np.abs(got - want).max()):.2e}"
 
 
 def test_stft_short_signal_raises(ctx):

@@ -40,13 +40,36 @@ class Prog:
         self.lines.append((name, expr))
         return name
 
-    # real ops
-    def add(self, a, b): return self.tmp(f"{a} + {b}")
-    def sub(self, a, b): return self.tmp(f"{a} - {b}")
-    def neg(self, a): return self.tmp(f"-{a}")
-    def mulc(self, a, c): return self.tmp(f"{a} * {self.const(c)}")
-    def mad(self, a, c, b): return self.tmp(f"{a} * {self.const(c)} + {b}")      # a*c + b
-    def msub(self, a, c, b): return self.tmp(f"{b} - {a} * {self.const(c)}")     # b - a*c
+    # real ops (ZERO is a symbolic exact zero: real-input codelets feed it as every imaginary part and the
+    # simplifications below remove the arithmetic it touches)
+    def add(self, a, b):
+        if a == ZERO: return b
+        if b == ZERO: return a
+        return self.tmp(f"{a} + {b}")
+
+    def sub(self, a, b):
+        if b == ZERO: return a
+        if a == ZERO: return self.neg(b)
+        return self.tmp(f"{a} - {b}")
+
+    def neg(self, a):
+        return ZERO if a == ZERO else self.tmp(f"-{a}")
+
+    def mulc(self, a, c):
+        return ZERO if a == ZERO else self.tmp(f"{a} * {self.const(c)}")
+
+    def mad(self, a, c, b):                                # a*c + b
+        if a == ZERO: return b
+        if b == ZERO: return self.mulc(a, c)
+        return self.tmp(f"{a} * {self.const(c)} + {b}")
+
+    def msub(self, a, c, b):                               # b - a*c
+        if a == ZERO: return b
+        if b == ZERO: return self.mulc(a, -c)
+        return self.tmp(f"{b} - {a} * {self.const(c)}")
+
+
+ZERO = "ZERO"
 
 
 def cadd(P, a, b): return (P.add(a[0], b[0]), P.add(a[1], b[1]))
@@ -165,6 +188,61 @@ def build(n):
     return P, outs
 
 
+def build_real(n, n_out):
+    """DFT of n REAL inputs, outputs 0 .. n_out-1 only (the rest follows from Hermitian symmetry)."""
+    P = Prog(n)
+    v = [(f"x{i}", ZERO) for i in range(n)]
+    outs = dft(P, v)[:n_out]
+    return P, outs
+
+
+def live_lines(P, outs):
+    """dead-code elimination: the lines the requested outputs depend on, in order"""
+    import re as _re
+    need = set()
+    for o in outs:
+        need.update(o)
+    keep = []
+    for name, expr in reversed(P.lines):
+        if name in need:
+            keep.append((name, expr))
+            need.update(_re.findall(r"[tx]\d+[ri]?", expr))
+    return list(reversed(keep))
+
+
+def verify_real(P, outs, n, trials=64):
+    rng = np.random.default_rng(n + 1)
+    x = rng.standard_normal((n, trials))
+    env = {f"x{i}": x[i].copy() for i in range(n)}
+    env.update(P.consts)
+    env[ZERO] = np.zeros(trials)
+    for name, expr in live_lines(P, outs):
+        env[name] = eval(expr, {}, env)
+    got = np.stack([env[o[0]] + 1j * env[o[1]] for o in outs])
+    want = np.fft.fft(x, axis=0)[:len(outs)]
+    return float(np.abs(got - want).max() / np.abs(want).max())
+
+
+def emit_real(P, outs, n):
+    lines_ = live_lines(P, outs)
+    ops = sum(1 for _, e in lines_ if not e.startswith("-"))
+    lines = [f"// real-input DFT-{n}, outputs 0..{len(outs) - 1}: {ops} float operations (before FMA contraction)",
+             f"__device__ __forceinline__ void rdft{n}(const float (&x)[{n}], float2 (&y)[{len(outs)}]) {{"]
+    used = " ".join(e for _, e in lines_)
+    for k, val in P.consts.items():
+        if k in used.split() or any(k == tok for tok in used.replace("-", " ").split()):
+            lines.append(f"  constexpr float {k} = {val:.17g}f;")
+    for i in range(n):
+        lines.append(f"  const float x{i} = x[{i}];")
+    for name, expr in lines_:
+        lines.append(f"  const float {name} = {expr};")
+    for k, o in enumerate(outs):
+        re_, im_ = (("0.f" if c == ZERO else c) for c in o)
+        lines.append(f"  y[{k}] = make_float2({re_}, {im_});")
+    lines.append("}")
+    return "\n".join(lines)
+
+
 def verify(P, outs, n, trials=64):
     rng = np.random.default_rng(n)
     x = rng.standard_normal((n, trials)) + 1j * rng.standard_normal((n, trials))
@@ -210,6 +288,14 @@ def main():
         if err > 1e-12:
             raise SystemExit(f"verification failed for DFT-{n}")
         chunks.append(emit(P, outs, n))
+        chunks.append("")
+    for n, n_out in ((20, 11),):
+        P, outs = build_real(n, n_out)
+        err = verify_real(P, outs, n)
+        print(f"real DFT-{n} ({n_out} outputs): {len(live_lines(P, outs))} ops, max rel err {err:.2e}", file=sys.stderr)
+        if err > 1e-12:
+            raise SystemExit(f"verification failed for real DFT-{n}")
+        chunks.append(emit_real(P, outs, n))
         chunks.append("")
     chunks.append("template <int N> struct Dft;")
     for n in [int(s) for s in args.sizes.split(",")]:
