@@ -28,9 +28,19 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line: NCCL's version / debug banner (printed to stdout when NCCL_DEBUG is set in the
-# environment) goes to stderr instead
+# stdout carries exactly one JSON line: while the job runs, file descriptor 1 points at stderr (NCCL prints its version
+# banner with a plain printf when NCCL_DEBUG=VERSION is in the environment); emit() restores it for the result line
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -142,7 +152,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -344,7 +354,7 @@ def run_gpu(args):
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
