@@ -347,35 +347,48 @@ stft_r400_kernel(const float* __restrict__ wave, const int64_t* __restrict__ sam
     }
     __syncthreads();
 
-    // ---- pass 2: twiddle W_400^(b k1), DFT-20 over b, |.| straight to global memory
+    // ---- pass 2: twiddle W_400^(b k1), DFT-20 over b, |.| straight to global memory.
+    // Groups 0 and 1 (one warp) take k1 = 0 and k1 = 10, whose inputs are real (the .x / .y halves of slot 0) and
+    // whose outputs beyond k2 = 10 / 9 repeat rows already covered; groups 2..10 take k1 = 1..9.
     if (live && g <= 10) {
-        const int k1 = g;
-        const bool first = k1 == 0, last = k1 == 10;
-        const float2* zp = Z + fr * ZS + (last ? 0 : 20 * k1);
-        const float4* tq = reinterpret_cast<const float4*>(tw_r + k1 * 20);
-        float2 v[20];
-#pragma unroll
-        for (int b2 = 0; b2 < 10; ++b2) {
-            const float4 w4 = __ldg(tq + b2);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int b = 2 * b2 + h;
-                const float2 a = zp[b];
-                const float re = last ? a.y : a.x;
-                const float im = (first || last) ? 0.f : a.y;
-                const float wx = h ? w4.z : w4.x, wy = h ? w4.w : w4.y;
-                v[b] = (b == 0) ? make_float2(re, im) : make_float2(re * wx - im * wy, re * wy + im * wx);
-            }
-        }
-        Dft<20>::run(v);
         char* Sg = reinterpret_cast<char*>(S + base);
         const int T4 = 4 * T;
-        const int kmax = first ? 10 : (last ? 9 : 19);          // the other outputs of k1 = 0, 10 repeat rows already covered
+        float2 v[20];
+        if (g < 2) {                                            // warp-uniform
+            const int k1 = 10 * g;
+            const float* zr = reinterpret_cast<const float*>(Z + fr * ZS) + g;
+            const float4* tq = reinterpret_cast<const float4*>(tw_r + k1 * 20);
 #pragma unroll
-        for (int k2 = 0; k2 < 20; ++k2) {
-            const int row = (k2 < 10) ? k1 + 20 * k2 : 20 * (20 - k2) - k1;      // bin, or its mirror 400 - bin
-            if (k2 <= kmax)
+            for (int b2 = 0; b2 < 10; ++b2) {
+                const float4 w4 = __ldg(tq + b2);
+                const float r0 = zr[2 * (2 * b2)], r1 = zr[2 * (2 * b2 + 1)];
+                v[2 * b2] = make_float2(r0 * w4.x, r0 * w4.y);
+                v[2 * b2 + 1] = make_float2(r1 * w4.z, r1 * w4.w);
+            }
+            Dft<20>::run(v);
+            const int kmax = 10 - g;
+#pragma unroll
+            for (int k2 = 0; k2 <= 10; ++k2)
+                if (k2 <= kmax)
+                    *reinterpret_cast<float*>(Sg + (int64_t)(k1 + 20 * k2) * T4) =
+                        fast_sqrt(v[k2].x * v[k2].x + v[k2].y * v[k2].y);
+        } else {
+            const int k1 = g - 1;
+            const float2* zp = Z + fr * ZS + 20 * k1;
+            const float4* tq = reinterpret_cast<const float4*>(tw_r + k1 * 20);
+#pragma unroll
+            for (int b2 = 0; b2 < 10; ++b2) {
+                const float4 w4 = __ldg(tq + b2);
+                const float2 a0 = zp[2 * b2], a1 = zp[2 * b2 + 1];
+                v[2 * b2] = (b2 == 0) ? a0 : make_float2(a0.x * w4.x - a0.y * w4.y, a0.x * w4.y + a0.y * w4.x);
+                v[2 * b2 + 1] = make_float2(a1.x * w4.z - a1.y * w4.w, a1.x * w4.w + a1.y * w4.z);
+            }
+            Dft<20>::run(v);
+#pragma unroll
+            for (int k2 = 0; k2 < 20; ++k2) {
+                const int row = (k2 < 10) ? k1 + 20 * k2 : 20 * (20 - k2) - k1;      // bin, or its mirror 400 - bin
                 *reinterpret_cast<float*>(Sg + (int64_t)row * T4) = fast_sqrt(v[k2].x * v[k2].x + v[k2].y * v[k2].y);
+            }
         }
     }
 }
