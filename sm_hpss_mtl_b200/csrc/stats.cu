@@ -357,7 +357,8 @@ static int launch_moments_impl(hpss_ctx* ctx, const hpss_batch* b, float* feat, 
         // equal short clips: constant strides, no per-clip table lookups (moments_uniform_kernel)
         const int T = (int)b->uniform_frames;
         const int rg = (D + kWarps - 1) / kWarps;
-        int want = (ctx->sm_count * 48 + rg - 1) / rg;               // ~48 CTAs per SM in total
+        static const int ctas_per_sm = [] { const char* e = getenv("HPSS_MOM_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 16; }();
+        int want = (ctx->sm_count * ctas_per_sm + rg - 1) / rg;      // ~16 CTAs per SM in total (48: 0.110 ms, 16: 0.103 ms, 8: 0.107 ms on configs[1])
         int per = (b->n_clips + want - 1) / want;
         per = std::max(8, (per + 3) / 4 * 4);
         dim3 grid((unsigned)((b->n_clips + per - 1) / per), (unsigned)rg);
