@@ -6,16 +6,23 @@
 
 Workload (BASELINE.json configs[1]): a batch of 4096 synthetic 1 s 16 kHz segments per GPU,
 n_fft = 400, hop = 160, median kernels 31/31, 120 mel bands, feature LogMelHarmPercSpec.
-One step = waveform -> (240, 98) float32 featuregram for every clip of the batch + the raw
-feature moments of get_data_stats (hpss_featuregram_moments) (all-reduced over ranks when N > 1: the only collective).
+One step = waveform -> (240, 98) float32 featuregram for every clip of the batch + the raw feature moments of
+get_data_stats accumulated on the device (hpss_featuregram_moments); the K steps are K batches of one corpus pass,
+whose moment vector is all-reduced over the ranks ONCE, after the last batch and inside the timed region (the only
+collective; the reference needs the statistics once per corpus, lib/preprocessing.py:461-586).
 
-  value  device-resident waveform -> device-resident features, CUDA events on the launching
-         stream, max over ranks; inputs (262 MB) + intermediates (1.3 GB/step) exceed the
-         126 MB L2, so no explicit flush is needed between iterations.
-  e2e    the same through the host-buffer C-ABI entry (hpss_featuregram_host): pinned host
-         waveform in, pinned host features out, H2D and D2H inside the timed region.
+  value      device-resident waveform -> device-resident features, CUDA events on the launching stream, max over
+             ranks; inputs (262 MB) + intermediates (1.3 GB/step) exceed the 126 MB L2: no explicit flush needed.
+  e2e        the same through the host-buffer C-ABI entry (hpss_featuregram_host): pinned host waveform in, pinned
+             host features out, H2D and D2H inside the timed region; `probe` = the same bytes moved by bare
+             cudaMemcpyAsync (all ranks at once), i.e. what the box's host links allow.
+  e2e_stats  the get_data_stats shape: 16-bit PCM in host memory -> upload -> signal preparation (N2) -> features
+             -> moments; 8 KB come back (hpss_pipeline_run without a feature buffer).
+  sustained  >= 5 s of back-to-back steps with the clocks / power seen meanwhile.
   roofline / stages   per-kernel CUDA-event times from a separate pass over the same batch.
   cpu_baseline        oracle (librosa's algorithm on scipy/numpy) on all host cores, bounded sample.
+  dropin     wall time of the reference-signature calls: get_featuregram on one 10 s clip (configs[0]) next to the
+             oracle on one core, and featuregram_batch on a 64-file mini-batch.
 """
 from __future__ import annotations
 
@@ -111,7 +118,7 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, pw = [], [], set(), []
         for t, ln in self.lines:
             if (t0 is not None and t < t0) or (t1 is not None and t > t1):
                 continue                      # only samples taken while the GPU was under this benchmark's load
@@ -122,12 +129,18 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3]))
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "power_w_median": None,
+                    "power_w_max": None}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_median": statistics.median(pw) if pw else None, "power_w_max": max(pw) if pw else None}
 
 
 # ============================================================================= CPU arm
@@ -137,7 +150,17 @@ def run_reference(args):
         return 0            # one CPU arm per box: the other ranks exit without work
     from oracle.cpu_baseline import CpuArm, usable_cores
     cores = usable_cores()
-    per_core = args.cpu_clips_per_core or 64
+    # the whole 4096-clip batch per step when (steps + warmup) of it fit ~4 minutes, else the largest power-of-two
+    # fraction that does (throughput-normalised metric; the sample is stated in the line)
+    per_core = args.cpu_clips_per_core or -(-CFG["n_clips"] // cores)
+    n_steps = args.steps + max(args.warmup, 1)
+    if not args.cpu_clips_per_core:
+        probe = CpuArm(CFG, cores=cores, n_per_worker=8)
+        probe.step()
+        t8 = probe.step()
+        probe.close()
+        while per_core > 16 and t8 * per_core / 8 * n_steps > 240.0:
+            per_core = (per_core + 1) // 2
     arm = CpuArm(CFG, cores=cores, n_per_worker=per_core)
     for _ in range(max(args.warmup, 1)):
         arm.step()
@@ -146,7 +169,7 @@ def run_reference(args):
     audio_s = arm.clips_per_step * CFG["clip_samples"] / CFG["fs"]
     total = sum(times)
     value = audio_s * args.steps / total
-    sample = (f"{arm.clips_per_step} of the 4096 clips per step ({cores} single-threaded workers x "
+    sample = (f"{arm.clips_per_step} clips per step of the 4096-clip workload ({cores} single-threaded workers x "
               f"{per_core} clips), oracle = librosa algorithm on scipy.ndimage/numpy.fft/np.dot")
     line = {
         "impl": "reference", "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
@@ -170,9 +193,19 @@ def cpu_baseline_block(args):
     t = sum(arm.step() for _ in range(reps))
     arm.close()
     audio_s = arm.clips_per_step * CFG["clip_samples"] / CFG["fs"] * reps
-    return {"value": audio_s / t, "unit": "audio-s/s", "cores": cores, "kind": "port",
+    base = {"value": audio_s / t, "unit": "audio-s/s", "cores": cores, "kind": "port",
             "sample": f"{arm.clips_per_step} clips x {reps} passes of the same 1 s workload on {cores} single-threaded "
                       f"workers ({t:.1f} s of wall time); oracle = librosa algorithm on scipy/numpy"}
+    # configs[0]: one 10 s clip, k = 21 / 11, on ONE core (what a reference user waits for per file)
+    from oracle import preprocessing_oracle as po
+    from sm_hpss_mtl_b200 import synth
+    y = synth.synth_clip(7, 160000)
+    po.featuregram(y[:32000], 16000, 25, 10, 21, 11, 400, 120, "LogMelHarmPercSpec")
+    t0 = time.perf_counter()
+    for _ in range(3):
+        po.featuregram(y, 16000, 25, 10, 21, 11, 400, 120, "LogMelHarmPercSpec")
+    base["one_10s_clip_ms_1core"] = 1e3 * (time.perf_counter() - t0) / 3
+    return base
 
 
 def bind_to_gpu_numa_node(local):
@@ -242,37 +275,75 @@ def run_gpu(args):
     acc = torch.zeros(3 * D + D + 3 + 1, dtype=torch.float64, device="cuda")
 
     def step():
-        acc.zero_()
-        engine.featuregram_moments(batch, wave, prm, classes, 3, out=out, acc=acc)
-        if world > 1:
-            allreduce_moments(acc)
+        engine.featuregram_moments(batch, wave, prm, classes, 3, out=out, acc=acc)      # accumulates into acc
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sampler = ClockSampler(local)
     sampler.start()                      # nvidia-smi needs a moment to come up: start it before the warm-up
     for _ in range(max(args.warmup, 3)):
         step()
+    if world > 1:
+        allreduce_moments(acc)           # communicator warm-up
     barrier()
     t_load0 = time.perf_counter()
     l0 = engine.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acc.zero_()
     barrier()
     ev0.record()
     for _ in range(args.steps):
         step()
+    if world > 1:
+        allreduce_moments(acc)           # the one collective of the corpus pass
     ev1.record()
     barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = engine.launch_count() - l0
+
+    # ---- sustained: the same step back to back for >= 5 s (clocks and power settle; no collective inside)
+    sus_sampler = ClockSampler(local)
+    sus_sampler.start()
+    time.sleep(0.3)
+    n_block = max(50, int(200.0 / max(ms_total / args.steps, 0.05)))     # ~0.2 s of steps between host checks
+    barrier()
+    t_s0 = time.perf_counter()
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es0.record()
+    n_sus = 0
+    while True:
+        for _ in range(n_block):
+            step()
+        n_sus += n_block
+        torch.cuda.synchronize()
+        if time.perf_counter() - t_s0 >= args.sustained_seconds:
+            break
+    es1.record()
+    torch.cuda.synchronize()
+    t_s1 = time.perf_counter()
+    sus_ms = es0.elapsed_time(es1)
+    sus_clocks = sus_sampler.stop(t_s0 + 0.5, t_s1)
+    # every rank ran its own count of steps for the same wall time: aggregate = sum of per-rank rates
+    sus_rate = n_sus * audio_s / (sus_ms * 1e-3)
     if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    # keep the sampler running over the e2e region as well (both are "under load")
+        t = torch.tensor([sus_rate], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        sus_rate = float(t.item())
+    sustained = {"seconds": round(sus_ms * 1e-3, 2), "steps_rank0": n_sus, "ms_per_step": sus_ms / n_sus,
+                 "value": sus_rate, "unit": "audio-s/s", "sm_mhz_median": sus_clocks["sm_mhz"],
+                 "sm_max_mhz": sus_clocks["sm_max_mhz"], "power_w_median": sus_clocks["power_w_median"],
+                 "power_w_max": sus_clocks["power_w_max"], "reasons": sus_clocks["reasons"],
+                 "samples": sus_clocks["samples"]}
 
     # ---- e2e: host buffers through the C-ABI host entry
     for _ in range(2):
@@ -284,11 +355,49 @@ def run_gpu(args):
         engine.featuregram_host(batch, wave_host, prm, out_host)
         _ = float(out_host[0])                     # the result is in host memory
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+
+    # ---- probe: the same bytes by bare pinned copies (H2D and D2H at once, every rank at the same time): the bound
+    # the host side of this box puts on e2e, whatever the kernels do
+    def copy_probe(h2d_host, d2h_host, reps):
+        d_in = torch.empty(h2d_host.size, dtype=torch.from_numpy(h2d_host[:1]).dtype, device="cuda")
+        d_out = torch.empty(max(d2h_host.size, 1), dtype=torch.float32, device="cuda") if d2h_host is not None else None
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        t_in, t_out = torch.from_numpy(h2d_host), (torch.from_numpy(d2h_host) if d2h_host is not None else None)
+
+        def once():
+            with torch.cuda.stream(s_in):
+                d_in.copy_(t_in, non_blocking=True)
+            if t_out is not None:
+                with torch.cuda.stream(s_out):
+                    t_out.copy_(d_out, non_blocking=True)
+            s_in.synchronize(); s_out.synchronize()
+        once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+        return max_over_ranks(time.perf_counter() - t0) / reps
+
+    probe_s = copy_probe(wave_host, out_host, e2e_steps)
+
+    # ---- e2e_stats: decoded 16-bit PCM in host memory -> upload -> preparation (N2) -> features -> moments
+    pcm_host = engine.host_alloc(n_clips * L, np.int16)
+    pcm_host[:] = np.clip(np.round(wave_host * 30000.0), -32768, 32767).astype(np.int16)
+    spl = engine.Pipeline(ctx, [L] * n_clips, prm, pcm_dtype=np.int16, prepare=True, fs=CFG["fs"])
+    mom = np.zeros(3 * D + D + 3 + 1)
+    for _ in range(2):
+        spl.run(pcm_host, clip_class=classes, n_classes=3, moments=mom, want_features=False)
+    barrier()
+    ls0 = engine.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        spl.run(pcm_host, clip_class=classes, n_classes=3, moments=mom, want_features=False)
+    stats_s = max_over_ranks(time.perf_counter() - t0)
+    stats_launches = (engine.launch_count() - ls0) // e2e_steps
+    probe_stats_s = copy_probe(pcm_host, None, e2e_steps)
+    spl.close()
+
     extra = False
     t_wait = time.perf_counter()
     while sampler.proc is not None and sampler.count_since(t_load0) < 3 and time.perf_counter() - t_wait < 3.0:
@@ -301,17 +410,41 @@ def run_gpu(args):
     if extra:
         clocks["note"] = "timed region shorter than the sampling period: the same step was kept running (untimed) until 3 samples arrived"
 
+    # ---- drop-in wall times (rank 0, one GPU): the reference-signature calls a user of lib/preprocessing.py makes
+    dropin = None
+    if rank == 0 and world == 1:
+        from sm_hpss_mtl_b200 import preprocessing as pp
+        model = "Lemaire_et_al_MTL"
+        P = {"Tw": CFG["Tw"], "Ts": CFG["Ts"], "Model": model, "l_harm": {model: 21}, "l_perc": {model: 11},
+             "frame_level_scaling": False}
+        clip10 = (synth.synth_clip(7, 160000) * 30000).astype(np.int16)      # configs[0]: one 10 s file, decoded
+        loader = lambda path: clip10
+        for _ in range(3):
+            pp.get_featuregram(P, "speech", "/nonexistent", "/x/clip10.wav", "", -1, 400, 120, "LogMelHarmPercSpec",
+                               save_feat=False, loader=loader)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            fv = pp.get_featuregram(P, "speech", "/nonexistent", "/x/clip10.wav", "", -1, 400, 120, "LogMelHarmPercSpec",
+                                    save_feat=False, loader=loader)
+        t_one = (time.perf_counter() - t0) / 10
+        sigs = [wave_host[i * L:(i + 1) * L] for i in range(64)]
+        for _ in range(3):
+            pp.featuregram_batch(sigs, CFG["fs"], P, 400, 120, "LogMelHarmPercSpec")
+        t0 = time.perf_counter()
+        for _ in range(10):
+            pp.featuregram_batch(sigs, CFG["fs"], P, 400, 120, "LogMelHarmPercSpec")
+        t_64 = (time.perf_counter() - t0) / 10
+        dropin = {"get_featuregram_one_10s_file_ms": round(1e3 * t_one, 3), "shape": list(fv.shape),
+                  "includes": "decoded int16 PCM -> upload -> prep (N2) -> features (k = 21/11) -> download, wall clock",
+                  "featuregram_batch_64x1s_ms": round(1e3 * t_64, 3),
+                  "cpu_oracle_one_10s_file_ms_1core": None if cpu_base is None else round(cpu_base.get("one_10s_clip_ms_1core", 0.0), 1)}
+
     # ---- per-stage pass (rank 0 only reports it): same batch, one CUDA-event pair per kernel
     stages = None
     if rank == 0:
-        fused = os.environ.get("HPSS_USE_FUSED", "0") not in ("", "0")     # the path hpss_featuregram takes
-        if fused:
-            names = ["K1 stft_mag", "K2h median_time", "K2p+K3 perc_mask_mel_log", "K3b+K5 topdb_moments"]
-            bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F + 8 * M, 8 * M]
-        else:
-            names = ["K1 stft_mag", "K2h median_time", "K2p median_freq", "K3 mask_mel_log", "K3b+K5 topdb_moments"]
-            # K3b+K5 reads every feature once and writes back only the values the top_db clip changes: 8*M, not 16*M
-            bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F, 12 * F + 8 * M, 8 * M]
+        names = ["K1 stft_mag", "K2h median_time", "K2p median_freq", "K3 mask_mel_log", "K3b+K5 topdb_moments"]
+        # K3b+K5 reads every feature once and writes back only the values the top_db clip changes: 8*M, not 16*M
+        bytes_per_frame = [4 * CFG["hop"] + 4 * F, 8 * F, 8 * F, 12 * F + 8 * M, 8 * M]
         tot = [0.0] * len(names)
         reps = max(args.steps, 5)
         for it in range(reps + 2):
@@ -319,14 +452,10 @@ def run_gpu(args):
             evs[0].record()
             S = engine.stft_mag(batch, wave, CFG["n_fft"], CFG["win"], CFG["hop"]); evs[1].record()
             harm = engine.median_time(batch, S, F, CFG["l_harm"]); evs[2].record()
-            if fused:
-                o, cmax = engine.perc_mask_mel_log(batch, S, harm, F, CFG["l_perc"], 22050, M, log_power=1); evs[3].record()
-                nxt = 4
-            else:
-                perc = engine.median_freq(batch, S, F, CFG["l_perc"]); evs[3].record()
-                o, cmax = engine.mask_mel_log(batch, S, harm, perc, F, mel_sr=22050, n_mels=M, log_power=1); evs[4].record()
-                nxt = 5
-                del perc
+            perc = engine.median_freq(batch, S, F, CFG["l_perc"]); evs[3].record()
+            o, cmax = engine.mask_mel_log(batch, S, harm, perc, F, mel_sr=22050, n_mels=M, log_power=1); evs[4].record()
+            nxt = 5
+            del perc
             acc.zero_()
             engine.topdb_moments(batch, o, M, 2, cmax, 80.0, classes, 3, acc=acc); evs[nxt].record()
             torch.cuda.synchronize()
@@ -360,14 +489,31 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_gpu": n_clips, "frames_per_gpu": frames,
                        "l2": "inputs+intermediates per step (1.6 GB) exceed the 126 MB L2; no explicit flush",
-                       "step": "hpss_featuregram_moments = K1, K2h, K2p, K3, K3b+K5 (top_db clip and moments share one pass)"
-                               + (" + NCCL all-reduce of the 968-double moment vector" if world > 1 else "")},
+                       "step": "hpss_featuregram_moments = K1, K2h, K2p, K3, K3b+K5 (top_db clip and moments share one pass); "
+                               "the K steps are K batches of one corpus pass"
+                               + (", whose 968-double moment vector is NCCL-all-reduced once, inside the timed region" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(wave_host.nbytes),
                     "d2h_bytes_per_step": int(out_host.nbytes), "steps": e2e_steps,
                     "api": "hpss_featuregram_host (pinned host buffers, chunked H2D/compute/D2H pipeline)",
+                    "ms_per_call": 1e3 * e2e_s / e2e_steps,
+                    "probe": {"what": "the same H2D + D2H bytes by bare cudaMemcpyAsync on two streams, all ranks at once, "
+                                      "max over ranks", "ms": 1e3 * probe_s,
+                              "bound_audio_s_per_s": world * audio_s / probe_s,
+                              "e2e_frac_of_probe_bound": probe_s / (e2e_s / e2e_steps)},
                     "rank0_numa_node": numa_node},
+            "e2e_stats": {"value": world * audio_s * e2e_steps / stats_s, "unit": "audio-s/s",
+                          "what": "get_data_stats shape: 16-bit PCM in pinned host memory -> upload -> signal preparation "
+                                  "(N2) -> features -> moments on the device; the moment vector comes back",
+                          "api": "hpss_pipeline_run (prepare, no feature buffer)",
+                          "h2d_bytes_per_step": int(pcm_host.nbytes), "d2h_bytes_per_step": int(mom.nbytes),
+                          "ms_per_call": 1e3 * stats_s / e2e_steps, "gpu_launches_per_call": int(stats_launches),
+                          "probe_ms": 1e3 * probe_stats_s,
+                          "probe_bound_audio_s_per_s": world * audio_s / probe_stats_s},
+            "sustained": sustained,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
         }
+        if dropin is not None:
+            line["dropin"] = dropin
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         emit(line)
@@ -386,8 +532,10 @@ def main():
     ap.add_argument("--clips", type=int, default=CFG["n_clips"], help="clips per GPU (default: the named 4096)")
     ap.add_argument("--cpu-clips-per-core", type=int, default=0,
                     help="clips per worker and pass of the CPU legs (default: 256 for cpu_baseline = the whole 4096-clip "
-                         "workload on 16 cores, ~15 s; 64 per step for --impl reference)")
+                         "workload on 16 cores, ~15 s; for --impl reference the whole 4096-clip batch per step when the "
+                         "run fits ~4 minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=5.0)
     args = ap.parse_args()
     for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ.setdefault(v, "1")

@@ -48,6 +48,17 @@ enum hpss_status {
     HPSS_ERR_NOMEM = 6,
     HPSS_ERR_NONFINITE = 7       /* non-finite audio: librosa.util.valid_audio raises      */
 };
+/* HPSS_ERR_NEGATIVE / HPSS_ERR_NONFINITE are data-dependent: device entry points never synchronise, so the
+ * kernels that see the data (the signal preparation, hpss_validate_audio / hpss_validate_nonneg,
+ * hpss_featuregram_from_spec) set a bit in a device status word and hpss_ctx_check(), called where the
+ * caller synchronises anyway, turns it into the status.  The host-buffer entries (hpss_featuregram_host,
+ * hpss_pipeline_run) validate their input and return these codes themselves. */
+
+/* sample formats of decoded audio handed to the signal preparation */
+enum hpss_pcm_format {
+    HPSS_PCM_F32 = 0,            /* float32 samples (what librosa.load returns)             */
+    HPSS_PCM_S16 = 1             /* 16-bit PCM as stored in MUSAN's wav files; x / 32768 on the device */
+};
 
 /* Feature families of get_featuregram's name dispatch (lib/preprocessing.py:378-444).
  * The dispatch is by startswith(), so e.g. LogMelHarmSpec / LogMelPercSpec /
@@ -80,6 +91,7 @@ typedef struct hpss_params {
 
 typedef struct hpss_ctx hpss_ctx;       /* per-device context: tables + workspace            */
 typedef struct hpss_batch hpss_batch;   /* clip layout of one batch                          */
+typedef struct hpss_pipeline hpss_pipeline;   /* host-buffer pipeline: chunking + device slots */
 
 /* ---- library ------------------------------------------------------------------------ */
 HPSS_API const char* hpss_version(void);
@@ -92,6 +104,16 @@ HPSS_API int hpss_ctx_destroy(hpss_ctx* ctx);
 HPSS_API int hpss_ctx_device(const hpss_ctx* ctx);
 /* bytes of device workspace currently held by the context */
 HPSS_API uint64_t hpss_ctx_workspace_bytes(const hpss_ctx* ctx);
+/* Synchronises `stream` and returns HPSS_ERR_NONFINITE / HPSS_ERR_NEGATIVE if a kernel flagged such input since
+ * the last check (the status word is cleared), HPSS_OK otherwise.  The context owns one scratch workspace:
+ * entry points called from different streams or threads are serialised on the device through an event, so
+ * concurrent callers are safe but do not overlap. */
+HPSS_API int hpss_ctx_check(hpss_ctx* ctx, void* stream);
+/* librosa.util.valid_audio (stft raises "Audio buffer is not finite everywhere") and the non-negativity check of
+ * librosa.util.softmask as explicit passes for callers that hand device buffers of unknown content to the stage
+ * entry points; the outcome is reported by hpss_ctx_check. */
+HPSS_API int hpss_validate_audio(hpss_ctx* ctx, const float* wave_dev, int64_t n, void* stream);
+HPSS_API int hpss_validate_nonneg(hpss_ctx* ctx, const float* x_dev, int64_t n, void* stream);
 
 /* pinned host memory for hpss_featuregram_host callers */
 HPSS_API int hpss_host_alloc(void** ptr, uint64_t bytes);
@@ -166,16 +188,6 @@ HPSS_API int hpss_mask_mel_log_sr(hpss_ctx* ctx, const hpss_batch* batch, const 
                                   int32_t log_power, float amin, float* out_dev,
                                   uint32_t* clip_max_dev, void* stream);
 
-/* ---- K2p + K3 fused: the frequency-axis median of S (size k), both soft masks against harm_dev, S*mask,
- * the per-stream mel projection (Slaney basis for mel_sr and n_fft = 2*(rows-1); n_mels == 0 -> identity,
- * out rows = 2*rows) and power_to_db without the clip, in one kernel: the percussive median never leaves
- * the SM.  Bit-identical to hpss_median_freq followed by hpss_mask_mel_log.  HPSS_ERR_UNSUPPORTED when k
- * has no generated selection network (odd 3..63); hpss_featuregram then uses the separate kernels. */
-HPSS_API int hpss_perc_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* S_dev,
-                                    const float* harm_dev, int32_t rows, int32_t k, int32_t mel_sr,
-                                    int32_t n_mels, int32_t log_power, float amin, float* out_dev,
-                                    uint32_t* clip_max_dev, void* stream);
-
 /* ---- K3b: the top_db part of librosa.core.power_to_db: x = max(x, max_clip_stream - top_db)
  * (lib/preprocessing.py:388,401,420,422,441-442).  out rows = n_streams * rows_per_stream. */
 HPSS_API int hpss_topdb_clip(hpss_ctx* ctx, const hpss_batch* batch, float* out_dev,
@@ -198,26 +210,75 @@ HPSS_API int hpss_featuregram_from_spec(hpss_ctx* ctx, const hpss_batch* batch, 
 HPSS_API int hpss_featuregram_host(hpss_ctx* ctx, const hpss_batch* batch, const float* wave_host,
                                    const hpss_params* params, float* out_host);
 
+/* Host-buffer pipeline as an object (what hpss_featuregram_host runs internally), for corpus passes: clips are cut
+ * into ~n_chunks_hint chunks (0 = default 16; never splitting a clip); chunk i+1 uploads while chunk i computes and
+ * chunk i-1 downloads.
+ *   prepare == 0: pcm_host is the prepared float32 waveform (pcm_format must be HPSS_PCM_F32).
+ *   prepare != 0: pcm_host is the decoded file (float32 or int16 PCM); load_and_preprocess_signal's normalise /
+ *                 silence removal / normalise (lib/preprocessing.py:332-348, tools.pyx:42-134) runs on the device
+ *                 with frame_length = params->win_length, hop = params->hop_length, sampling rate fs.
+ * hpss_pipeline_run: feat_host (may be NULL: features are not downloaded) receives hpss_feature_rows(params) x
+ * total_frames floats in the batch layout; when clip_class_host / moments_host are given, the raw moments of
+ * get_data_stats ([n_classes*D sums | D sums of squares | n_classes frame counts | non-finite count], float64) are
+ * ADDED to moments_host -- the corpus pass of get_data_stats then moves 8 KB back instead of the features.
+ * Returns HPSS_ERR_NONFINITE for non-finite audio (librosa.util.valid_audio). */
+HPSS_API int hpss_pipeline_create(hpss_ctx* ctx, const int64_t* clip_len_host, int32_t n_clips,
+                                  const hpss_params* params, int32_t pcm_format, int32_t prepare, int32_t fs,
+                                  double alpha, double beta, int32_t n_chunks_hint, hpss_pipeline** pipeline);
+HPSS_API int hpss_pipeline_destroy(hpss_pipeline* pipeline);
+HPSS_API int64_t hpss_pipeline_total_frames(const hpss_pipeline* pipeline);
+HPSS_API int32_t hpss_pipeline_n_chunks(const hpss_pipeline* pipeline);
+HPSS_API int hpss_pipeline_frame_offsets(const hpss_pipeline* pipeline, int64_t* out_host);
+HPSS_API int hpss_pipeline_run(hpss_pipeline* pipeline, const void* pcm_host, float* feat_host,
+                               const int32_t* clip_class_host, int32_t n_classes, double* moments_host);
+
+/* ---- N2: signal preparation = load_and_preprocess_signal after the decode (lib/preprocessing.py:332-348):
+ * normalize_signal (:114-132), librosa.feature.rms(frame_length=win_length, hop_length, center=True) (:337),
+ * removeSilence (lib/cython_impl/tools.pyx:42-134: float32 threshold alpha*max, 5-tap median of the markers,
+ * stretches longer than beta seconds, nothing removed unless MORE than one stretch qualifies, kept samples packed
+ * to the front of a buffer of ones that keeps the original length), the doubling of clips shorter than 0.1 s
+ * (:345-347) and the second normalize_signal (:348), for n_clips files per call.
+ *   pcm_dev: the files back to back, float32 or int16 (hpss_pcm_format); out_dev: the prepared float32 signals back
+ *   to back, clip c has hpss_prep_out_length(len_c, fs) samples (== len_c unless len_c / fs < 0.1).
+ *   Optional outputs (NULL to skip): frame_marker_dev int32 per RMS frame (clip c owns hpss_prep_num_frames(len_c)
+ *   entries, clips back to back) = the reference's frame_silMarker; sample_marker_dev uint8 per input sample = its
+ *   sample_silMarker; n_sil_dev int32 per clip = stretches that qualified.
+ * Non-finite samples set the NONFINITE bit (hpss_ctx_check). */
+HPSS_API int64_t hpss_prep_out_length(int64_t n_samples, int32_t fs);
+HPSS_API int64_t hpss_prep_num_frames(int64_t n_samples, int32_t win_length, int32_t hop_length);
+HPSS_API int hpss_prep_signals(hpss_ctx* ctx, const void* pcm_dev, int32_t pcm_format, const int64_t* clip_len_host,
+                               int32_t n_clips, int32_t fs, int32_t win_length, int32_t hop_length, double alpha,
+                               double beta, float* out_dev, int32_t* frame_marker_dev, uint8_t* sample_marker_dev,
+                               int32_t* n_sil_dev, void* stream);
+/* mix_signals (lib/preprocessing.py:297-325) for n_pairs (speech, music) pairs: the music is looped to the speech
+ * length, scaled to the target speech-to-music ratio target_db_host[p] (dB), both weights divided by their sum, the
+ * mix normalised (normalize_signal).  sp_dev / mu_dev: prepared signals back to back with the given lengths; out_dev:
+ * the mixes back to back, pair p has sp_len_host[p] samples.  float64 arithmetic, one rounding to float32. */
+HPSS_API int hpss_mix_signals(hpss_ctx* ctx, const float* sp_dev, const int64_t* sp_len_host, const float* mu_dev,
+                              const int64_t* mu_len_host, const double* target_db_host, int32_t n_pairs,
+                              float* out_dev, void* stream);
+
 /* ---- K5: raw moments for get_data_stats (lib/preprocessing.py:461-586).
- * feat_dev: (D, T_c) per clip.  clip_class_host[c] in [0, n_classes).  Accumulates, in
+ * feat_dev: (D, T_c) per clip.  clip_class_host[c] in [0, n_classes), n_clips entries (must equal the batch's clip
+ * count; the classes stay on the device and are uploaded again only when they change).  Accumulates, in
  * float64, sum_dev[class*D + d] += sum_t x, sumsq_dev[d] += sum_t x^2 (all classes),
  * count_dev[class] += T_c, nonfinite_dev[0] += number of non-finite values.  The caller
  * zeroes the accumulators once, calls this per batch, all-reduces them across ranks (the
  * only collective on the path) and finishes with hpss_stats_finalize. */
 HPSS_API int hpss_moments(hpss_ctx* ctx, const hpss_batch* batch, const float* feat_dev, int32_t D,
-                          const int32_t* clip_class_host, int32_t n_classes, double* sum_dev,
+                          const int32_t* clip_class_host, int32_t n_clips, int32_t n_classes, double* sum_dev,
                           double* sumsq_dev, double* count_dev, double* nonfinite_dev, void* stream);
 /* K3b + K5 in one pass over the features: hpss_topdb_clip followed by hpss_moments of the clipped values. */
 HPSS_API int hpss_topdb_moments(hpss_ctx* ctx, const hpss_batch* batch, float* out_dev, int32_t rows_per_stream,
                                 int32_t n_streams, const uint32_t* clip_max_dev, float top_db,
-                                const int32_t* clip_class_host, int32_t n_classes, double* sum_dev,
+                                const int32_t* clip_class_host, int32_t n_clips, int32_t n_classes, double* sum_dev,
                                 double* sumsq_dev, double* count_dev, double* nonfinite_dev, void* stream);
 /* hpss_featuregram followed by hpss_moments in one call; when the feature has a top_db clip the
  * clip and the moment accumulation share a single pass over the features (K3b + K5 fused). */
 HPSS_API int hpss_featuregram_moments(hpss_ctx* ctx, const hpss_batch* batch, const float* wave_dev,
                                       const hpss_params* params, float* out_dev, const int32_t* clip_class_host,
-                                      int32_t n_classes, double* sum_dev, double* sumsq_dev, double* count_dev,
-                                      double* nonfinite_dev, void* stream);
+                                      int32_t n_clips, int32_t n_classes, double* sum_dev, double* sumsq_dev,
+                                      double* count_dev, double* nonfinite_dev, void* stream);
 /* class means -> unweighted mean of class means (:530-536); stdev = sqrt(sum (x-mean)^2 /
  * (N-1)) (:575-583) from the raw moments, float64 -> float32 (:586). Host arrays. */
 HPSS_API int hpss_stats_finalize(const double* sum_host, const double* sumsq_host,
@@ -243,6 +304,36 @@ HPSS_API int64_t hpss_num_patches(int64_t n_frames, int32_t patch_size, int32_t 
 HPSS_API int hpss_extract_patches(hpss_ctx* ctx, const float* feat_dev, int32_t D, int64_t n_frames,
                                   int32_t patch_size, int32_t patch_shift, double* out_dev,
                                   void* stream);
+
+/* N1, device resident: the model-ready patch tensor of a whole batch of featuregrams in one call -- what
+ * get_feature_patches (lib/preprocessing.py:137-292) followed by the generator's batch assembly builds on the host.
+ *   feat_dev   (D, T_c) float32 per clip in the batch layout (hpss_featuregram output); standardize != 0 first applies
+ *              hpss_row_standardize IN PLACE (the reference's StandardScaler(copy=False) also mutates its input).
+ *   rows       [row0, row0 + n_rows): all rows for *HarmPercSpec / the plain names (the per-stream scalers act per
+ *              row, so standardising both halves at once equals :211-224), [0, D/2) for *HarmSpec, [D/2, D) for *PercSpec.
+ *   patches    clip c contributes hpss_num_patches_tiled(T_c, W, shift) patches (clips shorter than W are tiled
+ *              along time like :139-142); hpss_patch_offsets returns the n_clips+1 prefix sums.
+ *   out_dev    time_major == 0: (n_patches, n_rows, W)  (CNN input, lib/proposed_architectures.py:451);
+ *              time_major != 0: (n_patches, W, n_rows)  (the transpose the TCNs take, Proposed_Work_Results.py:235-236);
+ *              float32 (out_f64 == 0, what the model consumes) or float64 (the reference's dtype, tools.pyx:27). */
+HPSS_API int64_t hpss_num_patches_tiled(int64_t n_frames, int32_t patch_size, int32_t patch_shift);
+HPSS_API int hpss_patch_offsets(const hpss_batch* batch, int32_t patch_size, int32_t patch_shift, int64_t* out_host);
+HPSS_API int hpss_patch_tensor(hpss_ctx* ctx, const hpss_batch* batch, float* feat_dev, int32_t D, int32_t standardize,
+                               int32_t row0, int32_t n_rows, int32_t patch_size, int32_t patch_shift,
+                               int32_t time_major, int32_t out_f64, void* out_dev, void* stream);
+
+/* get_data_stats drops, per file, the feature rows that hold a NaN or Inf (lib/preprocessing.py:507-508):
+ * flags_dev[c * D + d] = 1 when row d of clip c has a non-finite value.  Only needed when hpss_moments reported
+ * non-finite values. */
+HPSS_API int hpss_row_nonfinite(hpss_ctx* ctx, const hpss_batch* batch, const float* feat_dev, int32_t D,
+                                uint8_t* flags_dev, void* stream);
+
+/* N4: get_data_statistics (lib/cython_impl/tools.pyx:169-211): per-patch statistic vectors of a (n_patches, n_feat,
+ * n_frames) float64 patch array.  stat: 0 mean, 1 variance (ddof 0), 2 scipy.stats.skew, 3 scipy.stats.kurtosis
+ * (biased, Fisher).  axis 0 reduces over the features -> (n_patches, n_frames) ("percussive"); axis 1 over the
+ * frames -> (n_patches, n_feat) ("harmonic").  Constant vectors give NaN for skew / kurtosis as scipy >= 1.9 does. */
+HPSS_API int hpss_patch_statistics(hpss_ctx* ctx, const double* patches_dev, int64_t n_patches, int32_t n_feat,
+                                   int32_t n_frames, int32_t stat, int32_t axis, double* out_dev, void* stream);
 
 /* ---- extension: MFCC.  The reference has no MFCC / DCT anywhere; BASELINE.json's north_star
  * names it, so it is offered as what librosa.feature.mfcc would add after the reference's log-mel step

@@ -1,8 +1,8 @@
-"""CPU restatement of the reference's feature front-end glue (lib/preprocessing.py).
+"""CPU restatement of the reference's feature front-end glue (lib/preprocessing.py) and of the signal
+preparation in front of it.
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Works on waveforms already in
-memory (the reference's file loading / silence removal sit *before* the hot path,
-SURVEY.md section 8 row N2).  Function names follow the reference.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Works on waveforms already in memory.
+Function names follow the reference.
 """
 from __future__ import annotations
 
@@ -16,6 +16,92 @@ def normalize_signal(Xin):
     Xin = Xin - np.mean(Xin)
     Xin = Xin / np.max(np.abs(Xin))
     return Xin
+
+
+# ---- librosa.feature.rms(y, frame_length, hop_length, center=True, pad_mode='reflect')[0] (lib/preprocessing.py:337)
+def frame_rms(y, frame_length, hop_length):
+    yp = np.pad(y, int(frame_length // 2), mode='reflect')
+    n = 1 + (len(yp) - frame_length) // hop_length
+    idx = np.arange(frame_length)[:, None] + hop_length * np.arange(n)[None, :]
+    x = yp[idx]
+    return np.sqrt(np.mean(np.abs(x) ** 2, axis=0))
+
+
+# ---- lib/cython_impl/tools.pyx:42-134 (the Cython leaf load_and_preprocess_signal calls) -------------------
+def removeSilence(Xin, nSamples, energy, nFrames, fs, Tw, Ts, alpha=0.025, beta=0.075):
+    """Quirks kept: the energy threshold is a C float, nothing is removed unless MORE than one silent stretch
+    qualifies, and the returned signal keeps its original length -- the kept samples are packed to the front of a
+    float32 buffer of ones."""
+    from scipy.signal import medfilt
+    frameSize = int((Tw * fs) / 1000)
+    frameShift = int((Ts * fs) / 1000)
+    thresh = np.float32(alpha * np.max(energy))
+    marker = (np.asarray(energy) >= thresh).astype(np.float64)
+    marker = (medfilt(marker, 5) > 0.5).astype(np.int64)
+    sample_marker = np.ones(nSamples, dtype=np.int64)
+    total, nSil, i = 0, 0, 0
+    last = nFrames - 1
+    while i < nFrames:
+        # i: first silent frame at/after i (or the last frame); j: first active frame after it (or the last)
+        nz = np.flatnonzero(marker[i:] == 0)
+        i = i + int(nz[0]) if nz.size else last
+        nz = np.flatnonzero(marker[i:] == 1)
+        j = i + int(nz[0]) if nz.size else last
+        k = max(frameShift * (i - 1) + frameSize, 1)
+        l = min(frameShift * (j - 1) + frameSize, nSamples)
+        if (l - k) / fs > beta:
+            sample_marker[k:l] = 0
+            nSil += 1
+            total += int((l - k) / fs)          # the reference accumulates into a C int
+        i = j + 1
+    if nSil > 1:
+        keep = np.flatnonzero(sample_marker == 1)
+        out = np.ones(nSamples, dtype=np.float32)
+        out[:keep.size] = Xin[keep]
+    else:
+        out = Xin
+    return out, sample_marker, marker, total
+
+
+# ---- lib/preprocessing.py:297-325 ---------------------------------------------------------------------------
+def mix_signals(Xin_sp, Xin_mu, target_dB):
+    n_sp = len(Xin_sp)
+    reps = int(np.ceil(n_sp / len(Xin_mu))) if len(Xin_mu) < n_sp else 1
+    mu = np.tile(Xin_mu, reps) if reps > 1 else Xin_mu.copy()
+    common = min(n_sp, len(mu))
+    sp, mu = Xin_sp[:common], mu[:common]
+    e_sp = np.sum(np.power(sp, 2)) / len(sp)
+    e_mu = np.sum(np.power(mu, 2)) / len(mu)
+    g_mu = np.sqrt((e_sp / np.power(10, (target_dB / 10))) / e_mu)
+    g_sp = 1
+    tot = g_mu + g_sp
+    g_mu /= tot
+    g_sp /= tot
+    return normalize_signal(g_sp * sp + g_mu * mu)
+
+
+# ---- lib/preprocessing.py:330-350 after the decode ----------------------------------------------------------
+def load_and_preprocess_signal(Xin, Tw, Ts, fs=16000, details=False):
+    Xin = normalize_signal(np.asarray(Xin, dtype=np.float32))
+    frameSize = int((Tw * fs) / 1000)
+    frameShift = int((Ts * fs) / 1000)
+    energy = frame_rms(Xin, frameSize, frameShift)
+    silrem, sample_marker, frame_marker, _ = removeSilence(Xin, len(Xin), energy, len(energy), fs, Tw, Ts)
+    out = silrem.copy()
+    if len(out) / fs < 0.1:
+        while len(out) / fs < 0.1:
+            out = np.append(out, out)
+    out = normalize_signal(out)
+    if details:
+        return out, sample_marker, frame_marker, energy
+    return out
+
+
+# ---- lib/cython_impl/tools.pyx:169-211 ----------------------------------------------------------------------
+def get_data_statistics(FV, stat_type='skew', axis=0):
+    from scipy.stats import kurtosis, skew
+    fn = {'mean': np.mean, 'variance': np.var, 'skew': skew, 'kurtosis': kurtosis}[stat_type]
+    return np.stack([fn(np.squeeze(FV[i]), axis=axis) for i in range(FV.shape[0])]).astype(np.float64)
 
 
 # ---- lib/preprocessing.py:378-444 (body of get_featuregram after the signal is loaded)

@@ -27,6 +27,7 @@ class ParameterError(ValueError):
 
 
 OK, ERR_INVALID, ERR_SHORT_SIGNAL, ERR_UNSUPPORTED, ERR_CUDA, ERR_NEGATIVE, ERR_NOMEM, ERR_NONFINITE = range(8)
+PCM_F32, PCM_S16 = 0, 1
 
 FEATURES = {
     "SPEC": 0, "LOGSPEC": 1, "MELSPEC": 2, "LOGMELSPEC": 3,
@@ -73,20 +74,37 @@ PROTOTYPES = {
     "hpss_median_freq": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "hpss_mask_mel_log": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
     "hpss_mask_mel_log_sr": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
-    "hpss_perc_mask_mel_log": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp]),
     "hpss_topdb_clip": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp]),
     "hpss_feature_rows": (_i32, [C.POINTER(Params)]),
     "hpss_featuregram": (C.c_int, [_vp, _vp, _vp, C.POINTER(Params), _vp, _vp]),
     "hpss_featuregram_from_spec": (C.c_int, [_vp, _vp, _vp, _i32, C.POINTER(Params), _vp, _vp]),
     "hpss_featuregram_host": (C.c_int, [_vp, _vp, _vp, C.POINTER(Params), _vp]),
-    "hpss_moments": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "hpss_topdb_moments": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "hpss_featuregram_moments": (C.c_int, [_vp, _vp, _vp, C.POINTER(Params), _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "hpss_moments": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "hpss_topdb_moments": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "hpss_featuregram_moments": (C.c_int, [_vp, _vp, _vp, C.POINTER(Params), _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "hpss_ctx_check": (C.c_int, [_vp, _vp]),
+    "hpss_validate_audio": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "hpss_validate_nonneg": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "hpss_pipeline_create": (C.c_int, [_vp, _pi64, _i32, C.POINTER(Params), _i32, _i32, _i32, _f64, _f64, _i32, _pp]),
+    "hpss_pipeline_destroy": (C.c_int, [_vp]),
+    "hpss_pipeline_total_frames": (_i64, [_vp]),
+    "hpss_pipeline_n_chunks": (_i32, [_vp]),
+    "hpss_pipeline_frame_offsets": (C.c_int, [_vp, _pi64]),
+    "hpss_pipeline_run": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
+    "hpss_prep_out_length": (_i64, [_i64, _i32]),
+    "hpss_prep_num_frames": (_i64, [_i64, _i32, _i32]),
+    "hpss_prep_signals": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _i32, _i32, _i32, _f64, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "hpss_mix_signals": (C.c_int, [_vp, _vp, _pi64, _vp, _pi64, _vp, _i32, _vp, _vp]),
     "hpss_stats_finalize": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "hpss_scale_data": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _f64, _vp, _vp]),
     "hpss_row_standardize": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "hpss_num_patches": (_i64, [_i64, _i32, _i32]),
     "hpss_extract_patches": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
+    "hpss_num_patches_tiled": (_i64, [_i64, _i32, _i32]),
+    "hpss_patch_offsets": (C.c_int, [_vp, _i32, _i32, _pi64]),
+    "hpss_patch_tensor": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "hpss_row_nonfinite": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    "hpss_patch_statistics": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "hpss_dct_mfcc": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "hpss_dct_basis": (C.c_int, [_i32, _i32, _vp]),
 }

@@ -19,7 +19,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libhpss_b200.so"
 OBJ = PKG / "_build"
-SOURCES = ["api.cu", "stft.cu", "stft_fast.cu", "median.cu", "median_walk.cu", "perc_mel_ws.cu", "maskmel.cu", "stats.cu", "dct.cu"]
+SOURCES = ["api.cu", "stft.cu", "stft_fast.cu", "median.cu", "median_walk.cu", "maskmel.cu", "stats.cu", "dct.cu", "prep.cu"]
 GEN_HEADER = CSRC / "median_networks_gen.cuh"
 GENERATOR = ROOT / "tools" / "gen_median_networks.py"
 FFT_HEADER = CSRC / "fft_codelets_gen.cuh"

@@ -30,6 +30,28 @@ int cuda_fail(cudaError_t e, const char* what) {
     return HPSS_ERR_CUDA;
 }
 
+// development knobs: the environment is read once, never on a launch path
+const Knobs& knobs() {
+    static const Knobs k = [] {
+        auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+        auto has = [](const char* name) { return getenv(name) != nullptr ? 1 : 0; };
+        Knobs v;
+        v.no_sweep = has("HPSS_NO_SWEEP");
+        v.host_chunks = std::max(0, geti("HPSS_HOST_CHUNKS", 0));
+        v.no_uniform_moments = has("HPSS_NO_UNIFORM_MOMENTS");
+        v.mom_ctas = geti("HPSS_MOM_CTAS", 16) > 0 ? geti("HPSS_MOM_CTAS", 16) : 16;
+        v.no_fast_stft = has("HPSS_NO_FAST_STFT");
+        v.no_uniform_stft = has("HPSS_NO_UNIFORM_STFT");
+        v.k1_real = geti("HPSS_K1_REAL", 1);
+        v.sweep1 = has("HPSS_SWEEP1");
+        v.sweep_u = geti("HPSS_SWEEP_U", 4);
+        v.dct_grid_mult = geti("HPSS_DCT_GRID_MULT", 8);
+        v.no_dense_median = has("HPSS_NO_DENSE_MEDIAN");
+        return v;
+    }();
+    return k;
+}
+
 // ---- host-side tables --------------------------------------------------------------
 static double hz_to_mel(double f) {
     const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
@@ -384,41 +406,17 @@ static int features_from_spec(hpss_ctx* ctx, const hpss_batch* b, const float* S
         if (rc) return rc;
     }
     const bool clip = is_log && p->top_db >= 0.f;
-    bool fused = false;
     if (ns == 2) {
         rc = launch_median(ctx, b, S, rows, p->l_harm, true, harm, st);
         if (rc) return rc;
-        // frequency median + soft masks + mel + log in one kernel when the kernel size has a generated
-        // selection network and the mel basis can be swept with two running sums
-        // (opt-in while it is not faster than the two separate kernels: HPSS_USE_FUSED=1)
-        static const int use_fused = getenv("HPSS_USE_FUSED") ? atoi(getenv("HPSS_USE_FUSED")) : 0;
-        if (use_fused) {
-            if (use_fused == 3 && mp) {   // warp-specialised walk + sweep (k = 15, 23, 31)
-                rc = launch_perc_mask_mel_ws(ctx, b, S, harm, rows, p->l_perc, mp, is_log ? 1 : 0, p->amin, out,
-                                             clip ? clip_max : nullptr, st, &fused);
-                if (rc) return rc;
-            }
-            if (!fused && use_fused != 2 && mp) {   // register walk + mel sweep (k = 15, 31)
-                rc = launch_perc_mask_mel_walk(ctx, b, S, harm, rows, p->l_perc, mp, is_log ? 1 : 0, p->amin, out,
-                                               clip ? clip_max : nullptr, st, &fused);
-                if (rc) return rc;
-            }
-            if (!fused) {
-                rc = launch_median_freq_fused(ctx, b, S, harm, rows, p->l_perc, mp, is_log ? 1 : 0, p->amin, out,
-                                              clip ? clip_max : nullptr, st, &fused);
-                if (rc) return rc;
-            }
-        }
-        if (!fused) {
-            rc = launch_median(ctx, b, S, rows, p->l_perc, false, perc, st);
-            if (rc) return rc;
-        }
+        rc = launch_median(ctx, b, S, rows, p->l_perc, false, perc, st);
+        if (rc) return rc;
     }
-    if (!fused) {
+    {
         const int pre_square = (ns == 1 && is_mel) ? 1 : 0;   // melspectrogram(y=..) uses |X|^2
         rc = launch_mask_mel(ctx, b, S, ns == 2 ? harm : nullptr, ns == 2 ? perc : nullptr, rows,
                              mp ? mp->d_w : nullptr, mp ? mp->d_band : nullptr,
-                             (mp && mp->sweepable && !getenv("HPSS_NO_SWEEP")) ? mp->d_sweep : nullptr,
+                             (mp && mp->sweepable && !knobs().no_sweep) ? mp->d_sweep : nullptr,
                              (mp && mp->walkable) ? mp->d_emit4 : nullptr, (mp && mp->walkable) ? mp->d_sweep_w : nullptr,
                              mp ? mp->n_mels : 0, pre_square,
                              is_log ? 1 : 0, p->amin, out, clip ? clip_max : nullptr, st);
@@ -516,6 +514,16 @@ int hpss_ctx_create(int device, hpss_ctx** out) {
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (ctx->sm_count <= 0) ctx->sm_count = kSMs;
+    cudaError_t e2 = cudaEventCreateWithFlags(&ctx->ws_done, cudaEventDisableTiming);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&ctx->d_flags, 4 * sizeof(uint32_t));
+    if (e2 == cudaSuccess) e2 = cudaMemset(ctx->d_flags, 0, 4 * sizeof(uint32_t));
+    if (e2 == cudaSuccess) e2 = cudaHostAlloc(&ctx->h_flags, 4 * sizeof(uint32_t), cudaHostAllocDefault);
+    if (e2 != cudaSuccess) {
+        if (ctx->ws_done) cudaEventDestroy(ctx->ws_done);
+        if (ctx->d_flags) cudaFree(ctx->d_flags);
+        delete ctx;
+        return cuda_fail(e2, "context status word");
+    }
     *out = ctx;
     return HPSS_OK;
 }
@@ -531,6 +539,10 @@ int hpss_ctx_destroy(hpss_ctx* ctx) {
     for (auto& kv : ctx->dct_plans) cudaFree(kv.second);
     for (auto& kv : ctx->mel_plans) { cudaFree(kv.second->d_w); cudaFree(kv.second->d_band); if (kv.second->d_sweep) cudaFree(kv.second->d_sweep); if (kv.second->d_emit4) cudaFree(kv.second->d_emit4); if (kv.second->d_sweep_w) cudaFree(kv.second->d_sweep_w); delete kv.second; }
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->prep_ws) cudaFree(ctx->prep_ws);
+    if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    if (ctx->ws_done) cudaEventDestroy(ctx->ws_done);
     if (ctx->band_scratch) cudaFree(ctx->band_scratch);
     for (int i = 0; i < 2; ++i) {
         if (ctx->pipe_dev[i]) cudaFree(ctx->pipe_dev[i]);
@@ -546,7 +558,7 @@ int hpss_ctx_destroy(hpss_ctx* ctx) {
 }
 
 int hpss_ctx_device(const hpss_ctx* ctx) { return ctx ? ctx->device : -1; }
-uint64_t hpss_ctx_workspace_bytes(const hpss_ctx* ctx) { return ctx ? ctx->ws_bytes + 2 * ctx->pipe_bytes : 0; }
+uint64_t hpss_ctx_workspace_bytes(const hpss_ctx* ctx) { return ctx ? ctx->ws_bytes + 2 * ctx->pipe_bytes + ctx->prep_ws_bytes : 0; }
 
 int hpss_host_alloc(void** ptr, uint64_t bytes) {
     if (!ptr) { set_error("ptr is NULL"); return HPSS_ERR_INVALID; }
@@ -596,7 +608,8 @@ int hpss_batch_destroy(hpss_batch* b) {
     if (b->d_stft_tiles) cudaFree(b->d_stft_tiles);
     if (b->d_clip_class) cudaFree(b->d_clip_class);
     for (auto& kv : b->time_tiles) if (kv.second.first) cudaFree(kv.second.first);
-    for (auto* s : b->host_chunks) hpss_batch_destroy(s);
+    for (auto& kv : b->patch_offs) if (kv.second.second) cudaFree(kv.second.second);
+    if (b->host_pipe) hpss_pipeline_destroy(b->host_pipe);
     delete b;
     return HPSS_OK;
 }
@@ -662,8 +675,12 @@ int hpss_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* S, co
     HPSS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     int2* band = nullptr;
+    ScratchLease lease;                          // band_scratch is context scratch
+    {
+        const int rc = lease.begin(ctx, st);
+        if (rc) return rc;
+    }
     if (mel) {
-        std::lock_guard<std::mutex> lk(ctx->mu);
         if (ctx->band_scratch_n < n_mels) {
             if (ctx->band_scratch) { HPSS_CUDA(cudaDeviceSynchronize()); HPSS_CUDA(cudaFree(ctx->band_scratch)); ctx->band_scratch = nullptr; }
             HPSS_CUDA(cudaMalloc(&ctx->band_scratch, sizeof(int2) * n_mels));
@@ -693,42 +710,6 @@ int hpss_mask_mel_log_sr(hpss_ctx* ctx, const hpss_batch* batch, const float* S,
                            pre_square, log_power, amin, out, clip_max, (cudaStream_t)stream);
 }
 
-int hpss_perc_mask_mel_log(hpss_ctx* ctx, const hpss_batch* batch, const float* S, const float* harm, int32_t rows,
-                           int32_t k, int32_t mel_sr, int32_t n_mels, int32_t log_power, float amin, float* out,
-                           uint32_t* clip_max, void* stream) {
-    if (!ctx || !batch || !S || !harm || !out) { set_error("perc_mask_mel_log: NULL argument"); return HPSS_ERR_INVALID; }
-    if (rows < 2 || k < 1 || n_mels < 0 || (n_mels > 0 && mel_sr < 1)) { set_error("perc_mask_mel_log: bad argument"); return HPSS_ERR_INVALID; }
-    if (log_power && !(amin > 0.f)) { set_error("amin must be strictly positive (librosa.power_to_db)"); return HPSS_ERR_INVALID; }
-    HPSS_CUDA(cudaSetDevice(ctx->device));
-    MelPlan* mp = nullptr;
-    if (n_mels > 0) {
-        int rc = get_mel_plan(ctx, mel_sr, 2 * (rows - 1), n_mels, &mp);
-        if (rc) return rc;
-    }
-    bool handled = false;
-    int rc = HPSS_OK;
-    if (mp && getenv("HPSS_WS")) {   // warp-specialised variant (measured slower than the single-warp walk: opt-in)
-        rc = launch_perc_mask_mel_ws(ctx, batch, S, harm, rows, k, mp, log_power, amin, out, clip_max,
-                                     (cudaStream_t)stream, &handled);
-        if (rc) return rc;
-    }
-    if (!handled && mp && !getenv("HPSS_NO_WALK")) {
-        rc = launch_perc_mask_mel_walk(ctx, batch, S, harm, rows, k, mp, log_power, amin, out, clip_max,
-                                       (cudaStream_t)stream, &handled);
-        if (rc) return rc;
-    }
-    if (!handled)
-        rc = launch_median_freq_fused(ctx, batch, S, harm, rows, k, mp, log_power, amin, out, clip_max,
-                                      (cudaStream_t)stream, &handled);
-    if (rc) return rc;
-    if (!handled) {
-        set_error("perc_mask_mel_log: k=%d has no generated selection network (odd 3..63) or the mel basis is not "
-                  "sweepable; use hpss_median_freq + hpss_mask_mel_log", k);
-        return HPSS_ERR_UNSUPPORTED;
-    }
-    return HPSS_OK;
-}
-
 int hpss_topdb_clip(hpss_ctx* ctx, const hpss_batch* batch, float* out, int32_t rows_per_stream, int32_t n_streams,
                     const uint32_t* clip_max, float top_db, void* stream) {
     if (!ctx || !batch || !out || !clip_max) { set_error("topdb_clip: NULL argument"); return HPSS_ERR_INVALID; }
@@ -747,6 +728,9 @@ int hpss_featuregram(hpss_ctx* ctx, const hpss_batch* batch, const float* wave, 
                      void* stream) {
     if (!ctx || !batch || !wave || !out) { set_error("featuregram: NULL argument"); return HPSS_ERR_INVALID; }
     HPSS_CUDA(cudaSetDevice(ctx->device));
+    ScratchLease lease;
+    int rc = lease.begin(ctx, (cudaStream_t)stream);
+    if (rc) return rc;
     return featuregram_device(ctx, const_cast<hpss_batch*>(batch), wave, p, out, (cudaStream_t)stream);
 }
 
@@ -763,170 +747,366 @@ int hpss_featuregram_from_spec(hpss_ctx* ctx, const hpss_batch* batch, const flo
                                   cudaMemcpyDeviceToDevice, st));
         return HPSS_OK;
     }
+    if (feature_streams(p->feature) == 2) {    // librosa.util.softmask raises on negative input: flagged for hpss_ctx_check
+        rc = launch_check(ctx, S, (int64_t)rows * batch->frame_off[batch->n_clips], 1, st);
+        if (rc) return rc;
+    }
+    ScratchLease lease;
+    rc = lease.begin(ctx, st);
+    if (rc) return rc;
     Workspace w;
     rc = carve_workspace(ctx, batch, rows, false, feature_streams(p->feature) == 2, 0, &w, nullptr);
     if (rc) return rc;
     return features_from_spec(ctx, batch, S, rows, p, w.harm, w.perc, w.clip_max, out, st);
 }
 
-// Host-buffer entry: clips are cut into chunks; chunk i+1 uploads while chunk i computes and
-// chunk i-1 downloads (three streams, two device slots).
+// ---- host-buffer pipeline ---------------------------------------------------------------------------------
+// Clips are cut into chunks (never splitting a clip); chunk i+1 uploads while chunk i computes and chunk i-1
+// downloads: three streams, two device slots.  Input is either the prepared float32 waveform or the decoded
+// file (float32 or int16 PCM) with the signal preparation of N2 run on the device; output is the features
+// in host memory and / or the raw moments of get_data_stats (the 8 KB a corpus pass really needs).
+static int ensure_pipe_streams(hpss_ctx* ctx) {
+    if (ctx->s_h2d) return HPSS_OK;
+    HPSS_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    HPSS_CUDA(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    HPSS_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        HPSS_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+        HPSS_CUDA(cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+        HPSS_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+    }
+    return HPSS_OK;
+}
+
+int hpss_pipeline_destroy(hpss_pipeline* pl) {
+    if (!pl) return HPSS_OK;
+    cudaSetDevice(pl->ctx->device);
+    cudaDeviceSynchronize();
+    for (auto* sb : pl->subs) if (sb) hpss_batch_destroy(sb);
+    for (int i = 0; i < 2; ++i) if (pl->slot[i]) cudaFree(pl->slot[i]);
+    if (pl->d_acc) cudaFree(pl->d_acc);
+    if (pl->h_acc) cudaFreeHost(pl->h_acc);
+    if (pl->d_class) cudaFree(pl->d_class);
+    delete pl;
+    return HPSS_OK;
+}
+
+int hpss_pipeline_create(hpss_ctx* ctx, const int64_t* clip_len, int32_t n_clips, const hpss_params* p,
+                         int32_t pcm_format, int32_t prepare, int32_t fs, double alpha, double beta,
+                         int32_t n_chunks_hint, hpss_pipeline** out) {
+    if (!ctx || !out || n_clips < 0 || (n_clips > 0 && !clip_len)) { set_error("pipeline_create: bad arguments"); return HPSS_ERR_INVALID; }
+    *out = nullptr;
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (pcm_format != HPSS_PCM_F32 && pcm_format != HPSS_PCM_S16) { set_error("pipeline_create: unknown pcm_format %d", pcm_format); return HPSS_ERR_INVALID; }
+    if (!prepare && pcm_format != HPSS_PCM_F32) { set_error("pipeline_create: int16 PCM needs prepare != 0 (the STFT reads float32)"); return HPSS_ERR_INVALID; }
+    if (prepare && fs < 1) { set_error("pipeline_create: fs=%d", fs); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    hpss_pipeline* pl = new hpss_pipeline();
+    pl->ctx = ctx; pl->prm = *p; pl->n_clips = n_clips; pl->pcm_format = pcm_format; pl->prepare = prepare; pl->fs = fs;
+    pl->alpha = alpha; pl->beta = beta;
+    pl->rows_out = hpss_feature_rows(p);
+    pl->in_len.assign(clip_len, clip_len + n_clips);
+    pl->in_off.assign(n_clips + 1, 0);
+    pl->wav_len.resize(n_clips);
+    pl->frame_off.assign(n_clips + 1, 0);
+    for (int c = 0; c < n_clips; ++c) {
+        pl->in_off[c + 1] = pl->in_off[c] + clip_len[c];
+        pl->wav_len[c] = prepare ? prep_out_length(clip_len[c], fs) : clip_len[c];
+        if (pl->wav_len[c] < p->n_fft) {
+            set_error("n_fft=%d is too large for input signal of length=%lld (clip %d)", p->n_fft, (long long)pl->wav_len[c], c);
+            delete pl;
+            return HPSS_ERR_SHORT_SIGNAL;
+        }
+        pl->frame_off[c + 1] = pl->frame_off[c] + 1 + (pl->wav_len[c] - p->n_fft) / p->hop_length;
+    }
+    // chunking: ~16 chunks, at least 1 M samples each, never splitting a clip
+    const int64_t total = pl->in_off[n_clips];
+    const int n_target = n_chunks_hint > 0 ? n_chunks_hint : (knobs().host_chunks > 0 ? knobs().host_chunks : 16);
+    const int64_t target = std::max<int64_t>(total / n_target, 1 << 20);
+    pl->cut.assign(1, 0);
+    for (int c = 0; c < n_clips;) {
+        int e = c;
+        int64_t acc = 0;
+        while (e < n_clips && (e == c || acc + clip_len[e] <= target)) { acc += clip_len[e]; ++e; }
+        pl->cut.push_back(e);
+        c = e;
+    }
+    const int n_chunks = (int)pl->cut.size() - 1;
+    pl->subs.assign(n_chunks, nullptr);
+    const int rows = p->n_fft / 2 + 1;
+    const size_t in_elt = pcm_format == HPSS_PCM_S16 ? 2 : 4;
+    for (int i = 0; i < n_chunks; ++i) {
+        const int c0 = pl->cut[i], c1 = pl->cut[i + 1];
+        rc = hpss_batch_from_samples(ctx, pl->wav_len.data() + c0, c1 - c0, p->n_fft, p->hop_length, &pl->subs[i]);
+        if (rc) { hpss_pipeline_destroy(pl); return rc; }
+        int64_t wav = 0;
+        for (int c = c0; c < c1; ++c) wav += pl->wav_len[c];
+        const int64_t frames = pl->frame_off[c1] - pl->frame_off[c0];
+        pl->in_bytes = std::max(pl->in_bytes, align256((size_t)(pl->in_off[c1] - pl->in_off[c0]) * in_elt));
+        pl->wav_bytes = std::max(pl->wav_bytes, align256((size_t)wav * 4));
+        pl->out_bytes = std::max(pl->out_bytes, align256((size_t)pl->rows_out * (size_t)frames * 4));
+        const size_t sz = align256((size_t)rows * (size_t)frames * sizeof(float));
+        pl->ws_need = std::max(pl->ws_need, 3 * sz + align256(sizeof(uint32_t) * 2 * (size_t)std::max(1, c1 - c0)));
+    }
+    const size_t slot_bytes = (prepare ? pl->in_bytes : 0) + pl->wav_bytes + pl->out_bytes;
+    for (int i = 0; i < 2 && n_chunks > 0; ++i) {
+        cudaError_t e = cudaMalloc(&pl->slot[i], std::max<size_t>(slot_bytes, 256));
+        if (e != cudaSuccess) { cudaGetLastError(); hpss_pipeline_destroy(pl); set_error("out of device memory: pipeline slot of %zu bytes", slot_bytes); return HPSS_ERR_NOMEM; }
+    }
+    *out = pl;
+    return HPSS_OK;
+}
+
+int64_t hpss_pipeline_total_frames(const hpss_pipeline* pl) { return pl ? pl->frame_off[pl->n_clips] : 0; }
+int32_t hpss_pipeline_n_chunks(const hpss_pipeline* pl) { return pl ? (int32_t)pl->subs.size() : 0; }
+int hpss_pipeline_frame_offsets(const hpss_pipeline* pl, int64_t* o) {
+    if (!pl || !o) { set_error("pipeline_frame_offsets: NULL argument"); return HPSS_ERR_INVALID; }
+    memcpy(o, pl->frame_off.data(), sizeof(int64_t) * (pl->n_clips + 1));
+    return HPSS_OK;
+}
+
+int hpss_pipeline_run(hpss_pipeline* pl, const void* pcm_host, float* feat_host, const int32_t* clip_class,
+                      int32_t n_classes, double* moments_host) {
+    if (!pl || !pcm_host) { set_error("pipeline_run: NULL argument"); return HPSS_ERR_INVALID; }
+    if ((clip_class == nullptr) != (moments_host == nullptr)) { set_error("pipeline_run: clip_class_host and moments_host go together"); return HPSS_ERR_INVALID; }
+    if (!feat_host && !moments_host) { set_error("pipeline_run: nothing to produce (feat_host and moments_host are NULL)"); return HPSS_ERR_INVALID; }
+    hpss_ctx* ctx = pl->ctx;
+    const hpss_params* p = &pl->prm;
+    const int n_chunks = (int)pl->subs.size();
+    if (n_chunks == 0) return HPSS_OK;
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensure_pipe_streams(ctx);
+    if (rc) return rc;
+    const int D = pl->rows_out;
+    const bool want_mom = moments_host != nullptr;
+    if (want_mom) {
+        if (n_classes < 1 || n_classes > 8) { set_error("pipeline_run: n_classes=%d (1..8)", n_classes); return HPSS_ERR_INVALID; }
+        for (int c = 0; c < pl->n_clips; ++c)
+            if (clip_class[c] < 0 || clip_class[c] >= n_classes) { set_error("clip %d has class %d outside [0,%d)", c, clip_class[c], n_classes); return HPSS_ERR_INVALID; }
+        const int n = n_classes * D + D + n_classes + 1;
+        if (pl->acc_n < n) {
+            if (pl->d_acc) { HPSS_CUDA(cudaFree(pl->d_acc)); pl->d_acc = nullptr; }
+            if (pl->h_acc) { HPSS_CUDA(cudaFreeHost(pl->h_acc)); pl->h_acc = nullptr; }
+            HPSS_CUDA(cudaMalloc(&pl->d_acc, sizeof(double) * n));
+            HPSS_CUDA(cudaHostAlloc(&pl->h_acc, sizeof(double) * n, cudaHostAllocDefault));
+            pl->acc_n = n;
+        }
+        if (!pl->d_class) HPSS_CUDA(cudaMalloc(&pl->d_class, sizeof(int32_t) * std::max(1, pl->n_clips)));
+    }
+    ScratchLease lease;                                   // the chunks share ctx->ws / prep_ws on s_comp
+    rc = lease.begin(ctx, ctx->s_comp);
+    if (rc) return rc;
+    rc = ensure_workspace(ctx, pl->ws_need);
+    if (rc) return rc;
+    const int n = n_classes * D + D + n_classes + 1;
+    if (want_mom) {
+        HPSS_CUDA(cudaMemsetAsync(pl->d_acc, 0, sizeof(double) * n, ctx->s_comp));
+        HPSS_CUDA(cudaMemcpyAsync(pl->d_class, clip_class, sizeof(int32_t) * pl->n_clips, cudaMemcpyHostToDevice, ctx->s_comp));
+    }
+    const size_t in_elt = pl->pcm_format == HPSS_PCM_S16 ? 2 : 4;
+    const char* src = (const char*)pcm_host;
+    for (int i = 0; i < n_chunks; ++i) {
+        const int s = i & 1;
+        const int c0 = pl->cut[i], c1 = pl->cut[i + 1];
+        char* base = (char*)pl->slot[s];
+        void* d_in = base;                                                    // raw PCM (prepare) or the waveform itself
+        float* d_wave = pl->prepare ? (float*)(base + pl->in_bytes) : (float*)base;
+        float* d_out = (float*)((char*)d_wave + pl->wav_bytes);
+        const size_t in_b = (size_t)(pl->in_off[c1] - pl->in_off[c0]) * in_elt;
+        const size_t os = (size_t)D * (size_t)(pl->frame_off[c1] - pl->frame_off[c0]);
+        cudaError_t e = cudaSuccess;
+        if (i >= 2) e = cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[s], 0);      // input slot free
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(d_in, src + (size_t)pl->in_off[c0] * in_elt, in_b, cudaMemcpyHostToDevice, ctx->s_h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_h2d[s], ctx->s_h2d);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[s], 0);
+        if (e == cudaSuccess && i >= 2 && feat_host) e = cudaStreamWaitEvent(ctx->s_comp, ctx->ev_d2h[s], 0);   // out slot free
+        if (e != cudaSuccess) { cudaDeviceSynchronize(); return cuda_fail(e, "host pipeline (upload)"); }
+        if (pl->prepare) {
+            rc = launch_prep(ctx, d_in, pl->pcm_format, pl->in_len.data() + c0, c1 - c0, pl->fs, p->win_length,
+                             p->hop_length, pl->alpha, pl->beta, d_wave, nullptr, nullptr, nullptr, ctx->s_comp);
+        } else {
+            int64_t wav = 0;
+            for (int c = c0; c < c1; ++c) wav += pl->wav_len[c];
+            rc = launch_check(ctx, d_wave, wav, 0, ctx->s_comp);               // librosa.util.valid_audio
+        }
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        MomentSink ms;
+        if (want_mom) {
+            ms.d_class = pl->d_class + c0; ms.n_classes = n_classes;
+            ms.sum = pl->d_acc; ms.sumsq = pl->d_acc + (size_t)n_classes * D;
+            ms.count = ms.sumsq + D; ms.nonfinite = ms.count + n_classes;
+        }
+        rc = featuregram_device(ctx, pl->subs[i], d_wave, p, d_out, ctx->s_comp, want_mom ? &ms : nullptr);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        e = cudaEventRecord(ctx->ev_comp[s], ctx->s_comp);
+        if (feat_host) {
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[s], 0);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(feat_host + (size_t)D * (size_t)pl->frame_off[c0], d_out, os * sizeof(float),
+                                    cudaMemcpyDeviceToHost, ctx->s_d2h);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_d2h[s], ctx->s_d2h);
+        }
+        if (e != cudaSuccess) { cudaDeviceSynchronize(); return cuda_fail(e, "host pipeline (download)"); }
+    }
+    cudaError_t e = cudaSuccess;
+    if (want_mom) e = cudaMemcpyAsync(pl->h_acc, pl->d_acc, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->s_comp);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_comp);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t), ctx->s_comp);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_comp);
+    if (e == cudaSuccess && feat_host) e = cudaStreamSynchronize(ctx->s_d2h);
+    if (e != cudaSuccess) return cuda_fail(e, "host pipeline (sync)");
+    if (want_mom)
+        for (int i = 0; i < n; ++i) moments_host[i] += pl->h_acc[i];
+    if (ctx->h_flags[0] & 1u) { set_error("Audio buffer is not finite everywhere"); return HPSS_ERR_NONFINITE; }
+    return HPSS_OK;
+}
+
+// Prepared float32 waveform in host memory -> features in host memory (the pipeline is cached in the batch).
 int hpss_featuregram_host(hpss_ctx* ctx, const hpss_batch* batch, const float* wave_host, const hpss_params* p,
                           float* out_host) {
     if (!ctx || !batch || !wave_host || !out_host) { set_error("featuregram_host: NULL argument"); return HPSS_ERR_INVALID; }
     int rc = check_params(p);
     if (rc) return rc;
     if (!batch->has_samples) { set_error("featuregram_host needs a batch built from sample lengths"); return HPSS_ERR_INVALID; }
-    HPSS_CUDA(cudaSetDevice(ctx->device));
-    if (!ctx->s_h2d) {
-        HPSS_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
-        HPSS_CUDA(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
-        HPSS_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            HPSS_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
-            HPSS_CUDA(cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
-            HPSS_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
-        }
+    if (batch->n_fft != p->n_fft || batch->hop != p->hop_length) {
+        set_error("batch was laid out for n_fft=%d hop=%d, params say %d / %d", batch->n_fft, batch->hop, p->n_fft, p->hop_length);
+        return HPSS_ERR_INVALID;
     }
     hpss_batch* pb = const_cast<hpss_batch*>(batch);
-    const int n = batch->n_clips;
-    const int rows_out = hpss_feature_rows(p);
-    if (pb->host_cut.empty()) {
-        // chunking: ~16 chunks, at least 4 M samples each, never splitting a clip
-        const int64_t total_samples = batch->sample_off[n];
-        const int n_target = getenv("HPSS_HOST_CHUNKS") ? std::max(1, atoi(getenv("HPSS_HOST_CHUNKS"))) : 16;   // development knob
-        const int64_t target = std::max<int64_t>(total_samples / n_target, 1 << 20);
-        std::vector<int> cut(1, 0);
-        for (int c = 0; c < n;) {
-            int e = c;
-            int64_t acc = 0;
-            while (e < n && (e == c || acc + (batch->sample_off[e + 1] - batch->sample_off[e]) <= target)) {
-                acc += batch->sample_off[e + 1] - batch->sample_off[e];
-                ++e;
-            }
-            cut.push_back(e);
-            c = e;
-        }
-        std::vector<hpss_batch*> subs(cut.size() - 1, nullptr);
-        for (size_t i = 0; i + 1 < cut.size(); ++i) {
-            std::vector<int64_t> len(cut[i + 1] - cut[i]);
-            for (int c = cut[i]; c < cut[i + 1]; ++c) len[c - cut[i]] = batch->sample_off[c + 1] - batch->sample_off[c];
-            rc = hpss_batch_from_samples(ctx, len.data(), (int)len.size(), batch->n_fft, batch->hop, &subs[i]);
-            if (rc) { for (auto* s : subs) if (s) hpss_batch_destroy(s); return rc; }
-        }
-        pb->host_cut = cut;
-        pb->host_chunks = subs;
-    }
-    const std::vector<int>& cut = pb->host_cut;
-    const std::vector<hpss_batch*>& subs = pb->host_chunks;
-    const int n_chunks = (int)cut.size() - 1;
-    size_t max_w = 0, max_o = 0;
-    for (int i = 0; i < n_chunks; ++i) {
-        max_w = std::max(max_w, (size_t)(batch->sample_off[cut[i + 1]] - batch->sample_off[cut[i]]));
-        max_o = std::max(max_o, (size_t)rows_out * (size_t)(batch->frame_off[cut[i + 1]] - batch->frame_off[cut[i]]));
-    }
-    const size_t slot_bytes = align256(max_w * sizeof(float)) + align256(max_o * sizeof(float));
-    if (slot_bytes > ctx->pipe_bytes) {
-        HPSS_CUDA(cudaDeviceSynchronize());
-        for (int i = 0; i < 2; ++i) {
-            if (ctx->pipe_dev[i]) { HPSS_CUDA(cudaFree(ctx->pipe_dev[i])); ctx->pipe_dev[i] = nullptr; }
-            HPSS_CUDA(cudaMalloc(&ctx->pipe_dev[i], slot_bytes));
-        }
-        ctx->pipe_bytes = slot_bytes;
-    }
-    auto cleanup = [&]() {};
-    // the shared compute workspace must be sized for the largest chunk before the pipeline starts
+    hpss_pipeline* pl = nullptr;
     {
-        size_t need = 0;
-        const int rows = p->n_fft / 2 + 1;
-        for (int i = 0; i < n_chunks; ++i) {
-            const size_t sz = align256((size_t)rows * (size_t)subs[i]->frame_off[subs[i]->n_clips] * sizeof(float));
-            need = std::max(need, 3 * sz + align256(sizeof(uint32_t) * 2 * (size_t)std::max(1, subs[i]->n_clips)));
+        std::lock_guard<std::mutex> lk(pb->mu);
+        if (pb->host_pipe && memcmp(&pb->host_pipe->prm, p, sizeof(*p)) != 0) { hpss_pipeline_destroy(pb->host_pipe); pb->host_pipe = nullptr; }
+        if (!pb->host_pipe) {
+            std::vector<int64_t> len(batch->n_clips);
+            for (int c = 0; c < batch->n_clips; ++c) len[c] = batch->sample_off[c + 1] - batch->sample_off[c];
+            rc = hpss_pipeline_create(ctx, len.data(), batch->n_clips, p, HPSS_PCM_F32, 0, 16000, 0.0, 0.0, 0, &pb->host_pipe);
+            if (rc) return rc;
         }
-        rc = ensure_workspace(ctx, need);
-        if (rc) { cleanup(); return rc; }
+        pl = pb->host_pipe;
     }
-    for (int i = 0; i < n_chunks; ++i) {
-        const int s = i & 1;
-        float* d_wave = (float*)ctx->pipe_dev[s];
-        float* d_out = (float*)((char*)ctx->pipe_dev[s] + align256(max_w * sizeof(float)));
-        const size_t ws = (size_t)(batch->sample_off[cut[i + 1]] - batch->sample_off[cut[i]]);
-        const size_t os = (size_t)rows_out * (size_t)(batch->frame_off[cut[i + 1]] - batch->frame_off[cut[i]]);
-        cudaError_t e = cudaSuccess;
-        if (i >= 2) e = cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[s], 0);      // wave slot free
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(d_wave, wave_host + batch->sample_off[cut[i]], ws * sizeof(float),
-                                cudaMemcpyHostToDevice, ctx->s_h2d);
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_h2d[s], ctx->s_h2d);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[s], 0);
-        if (e == cudaSuccess && i >= 2) e = cudaStreamWaitEvent(ctx->s_comp, ctx->ev_d2h[s], 0);   // out slot free
-        if (e != cudaSuccess) { cudaDeviceSynchronize(); cleanup(); return cuda_fail(e, "host pipeline (upload)"); }
-        rc = featuregram_device(ctx, subs[i], d_wave, p, d_out, ctx->s_comp);
-        if (rc) { cudaDeviceSynchronize(); cleanup(); return rc; }
-        e = cudaEventRecord(ctx->ev_comp[s], ctx->s_comp);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[s], 0);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(out_host + (size_t)rows_out * (size_t)batch->frame_off[cut[i]], d_out,
-                                os * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_d2h);
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_d2h[s], ctx->s_d2h);
-        if (e != cudaSuccess) { cudaDeviceSynchronize(); cleanup(); return cuda_fail(e, "host pipeline (download)"); }
-    }
-    cudaError_t e = cudaStreamSynchronize(ctx->s_d2h);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_comp);
-    cleanup();
-    if (e != cudaSuccess) return cuda_fail(e, "host pipeline (sync)");
-    return HPSS_OK;
+    return hpss_pipeline_run(pl, wave_host, out_host, nullptr, 0, nullptr);
 }
 
-static int upload_classes(hpss_batch* b, const int32_t* clip_class, int n_classes, cudaStream_t st) {
+// class per clip on the device, kept across calls (re-uploaded only when the classes change)
+static int upload_classes(hpss_batch* b, const int32_t* clip_class, int n_given, int n_classes, cudaStream_t st) {
+    if (n_given != b->n_clips) { set_error("clip_class has %d entries, the batch has %d clips", n_given, b->n_clips); return HPSS_ERR_INVALID; }
     for (int c = 0; c < b->n_clips; ++c)
         if (clip_class[c] < 0 || clip_class[c] >= n_classes) { set_error("clip %d has class %d outside [0,%d)", c, clip_class[c], n_classes); return HPSS_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(b->mu);
     if (!b->d_clip_class && b->n_clips > 0) HPSS_CUDA(cudaMalloc(&b->d_clip_class, sizeof(int32_t) * b->n_clips));
-    if (b->n_clips > 0)
-        HPSS_CUDA(cudaMemcpyAsync(b->d_clip_class, clip_class, sizeof(int32_t) * b->n_clips, cudaMemcpyHostToDevice, st));
+    if (b->n_clips > 0 && (b->h_clip_class.size() != (size_t)b->n_clips ||
+                           memcmp(b->h_clip_class.data(), clip_class, sizeof(int32_t) * b->n_clips) != 0)) {
+        b->h_clip_class.assign(clip_class, clip_class + b->n_clips);
+        HPSS_CUDA(cudaMemcpyAsync(b->d_clip_class, b->h_clip_class.data(), sizeof(int32_t) * b->n_clips, cudaMemcpyHostToDevice, st));
+    }
     return HPSS_OK;
 }
 
 int hpss_featuregram_moments(hpss_ctx* ctx, const hpss_batch* batch, const float* wave, const hpss_params* p,
-                             float* out, const int32_t* clip_class, int32_t n_classes, double* sum, double* sumsq,
-                             double* count, double* nonfinite, void* stream) {
+                             float* out, const int32_t* clip_class, int32_t n_clips, int32_t n_classes, double* sum,
+                             double* sumsq, double* count, double* nonfinite, void* stream) {
     if (!ctx || !batch || !wave || !out || !clip_class || !sum || !sumsq || !count || !nonfinite) { set_error("featuregram_moments: NULL argument"); return HPSS_ERR_INVALID; }
     if (n_classes < 1) { set_error("featuregram_moments: n_classes=%d", n_classes); return HPSS_ERR_INVALID; }
     HPSS_CUDA(cudaSetDevice(ctx->device));
     hpss_batch* b = const_cast<hpss_batch*>(batch);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = upload_classes(b, clip_class, n_classes, st);
+    int rc = upload_classes(b, clip_class, n_clips, n_classes, st);
     if (rc) return rc;
     MomentSink ms;
     ms.d_class = b->d_clip_class; ms.n_classes = n_classes;
     ms.sum = sum; ms.sumsq = sumsq; ms.count = count; ms.nonfinite = nonfinite;
+    ScratchLease lease;
+    rc = lease.begin(ctx, st);
+    if (rc) return rc;
     return featuregram_device(ctx, b, wave, p, out, st, &ms);
 }
 
 int hpss_topdb_moments(hpss_ctx* ctx, const hpss_batch* batch, float* out, int32_t rows_per_stream, int32_t n_streams,
-                       const uint32_t* clip_max, float top_db, const int32_t* clip_class, int32_t n_classes, double* sum,
-                       double* sumsq, double* count, double* nonfinite, void* stream) {
+                       const uint32_t* clip_max, float top_db, const int32_t* clip_class, int32_t n_clips,
+                       int32_t n_classes, double* sum, double* sumsq, double* count, double* nonfinite, void* stream) {
     if (!ctx || !batch || !out || !clip_max || !clip_class || !sum || !sumsq || !count || !nonfinite) { set_error("topdb_moments: NULL argument"); return HPSS_ERR_INVALID; }
     if (top_db < 0.f || rows_per_stream < 1 || n_streams < 1 || n_classes < 1) { set_error("topdb_moments: bad argument"); return HPSS_ERR_INVALID; }
     HPSS_CUDA(cudaSetDevice(ctx->device));
     hpss_batch* b = const_cast<hpss_batch*>(batch);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = upload_classes(b, clip_class, n_classes, st);
+    int rc = upload_classes(b, clip_class, n_clips, n_classes, st);
     if (rc) return rc;
     return launch_topdb_moments(ctx, batch, out, rows_per_stream, n_streams, clip_max, top_db, b->d_clip_class, n_classes,
                                 sum, sumsq, count, nonfinite, st);
 }
 
 int hpss_moments(hpss_ctx* ctx, const hpss_batch* batch, const float* feat, int32_t D, const int32_t* clip_class,
-                 int32_t n_classes, double* sum, double* sumsq, double* count, double* nonfinite, void* stream) {
+                 int32_t n_clips, int32_t n_classes, double* sum, double* sumsq, double* count, double* nonfinite,
+                 void* stream) {
     if (!ctx || !batch || !feat || !clip_class || !sum || !sumsq || !count || !nonfinite) { set_error("moments: NULL argument"); return HPSS_ERR_INVALID; }
     if (D < 1 || n_classes < 1) { set_error("moments: D=%d n_classes=%d", D, n_classes); return HPSS_ERR_INVALID; }
     HPSS_CUDA(cudaSetDevice(ctx->device));
     hpss_batch* b = const_cast<hpss_batch*>(batch);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = upload_classes(b, clip_class, n_classes, st);
+    int rc = upload_classes(b, clip_class, n_clips, n_classes, st);
     if (rc) return rc;
     return launch_moments(ctx, batch, feat, D, b->d_clip_class, n_classes, sum, sumsq, count, nonfinite, st);
+}
+
+// ---- N2: signal preparation -----------------------------------------------------------------------------------
+int64_t hpss_prep_out_length(int64_t n_samples, int32_t fs) { return fs > 0 ? prep_out_length(n_samples, fs) : 0; }
+int64_t hpss_prep_num_frames(int64_t n_samples, int32_t win, int32_t hop) { return prep_num_frames(n_samples, win, hop); }
+
+int hpss_prep_signals(hpss_ctx* ctx, const void* pcm, int32_t pcm_format, const int64_t* clip_len, int32_t n_clips,
+                      int32_t fs, int32_t win, int32_t hop, double alpha, double beta, float* out,
+                      int32_t* frame_marker, uint8_t* sample_marker, int32_t* n_sil, void* stream) {
+    if (!ctx || !pcm || !out || n_clips < 0 || (n_clips > 0 && !clip_len)) { set_error("prep_signals: NULL argument"); return HPSS_ERR_INVALID; }
+    if (pcm_format != HPSS_PCM_F32 && pcm_format != HPSS_PCM_S16) { set_error("prep_signals: unknown pcm_format %d", pcm_format); return HPSS_ERR_INVALID; }
+    if (fs < 1 || win < 1 || hop < 1) { set_error("prep_signals: fs=%d win_length=%d hop_length=%d", fs, win, hop); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    ScratchLease lease;
+    int rc = lease.begin(ctx, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_prep(ctx, pcm, pcm_format, clip_len, n_clips, fs, win, hop, alpha, beta, out, frame_marker,
+                       sample_marker, n_sil, (cudaStream_t)stream);
+}
+
+int hpss_mix_signals(hpss_ctx* ctx, const float* sp, const int64_t* sp_len, const float* mu, const int64_t* mu_len,
+                     const double* target_db, int32_t n_pairs, float* out, void* stream) {
+    if (!ctx || !sp || !mu || !out || n_pairs < 0 || (n_pairs > 0 && (!sp_len || !mu_len || !target_db))) { set_error("mix_signals: NULL argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    ScratchLease lease;
+    int rc = lease.begin(ctx, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_mix(ctx, sp, sp_len, mu, mu_len, target_db, n_pairs, out, (cudaStream_t)stream);
+}
+
+int hpss_validate_audio(hpss_ctx* ctx, const float* wave, int64_t n, void* stream) {
+    if (!ctx || (!wave && n > 0)) { set_error("validate_audio: NULL argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return launch_check(ctx, wave, n, 0, (cudaStream_t)stream);
+}
+
+int hpss_validate_nonneg(hpss_ctx* ctx, const float* x, int64_t n, void* stream) {
+    if (!ctx || (!x && n > 0)) { set_error("validate_nonneg: NULL argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return launch_check(ctx, x, n, 1, (cudaStream_t)stream);
+}
+
+// Synchronises `stream` and reports what the kernels flagged since the last check.
+int hpss_ctx_check(hpss_ctx* ctx, void* stream) {
+    if (!ctx) { set_error("ctx_check: NULL context"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t flags = 0;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        HPSS_CUDA(cudaMemcpyAsync(ctx->h_flags + 1, ctx->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        HPSS_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t), st));
+        HPSS_CUDA(cudaStreamSynchronize(st));
+        flags = ctx->h_flags[1];
+    }
+    if (flags & 1u) { set_error("Audio buffer is not finite everywhere"); return HPSS_ERR_NONFINITE; }
+    if (flags & 2u) { set_error("X and X_ref must be non-negative"); return HPSS_ERR_NEGATIVE; }
+    return HPSS_OK;
 }
 
 int hpss_stats_finalize(const double* sum, const double* sumsq, const double* count, int32_t D, int32_t n_classes,
@@ -982,6 +1162,73 @@ int64_t hpss_num_patches(int64_t n_frames, int32_t W, int32_t shift) {
     const int64_t half = W / 2;
     const int64_t a = half, b = n_frames - half;
     return b > a ? (b - a + shift - 1) / shift : 0;
+}
+
+// patches of one clip of T frames, including the tiling of clips shorter than the patch (lib/preprocessing.py:139-142)
+int64_t hpss_num_patches_tiled(int64_t T, int32_t W, int32_t shift) {
+    if (T < 1 || W < 1 || shift < 1) return 0;
+    int64_t Tt = T;
+    if (T < W) Tt = T * (W / T + 1);          // FV is appended to itself while its length is <= W
+    return hpss_num_patches(Tt, W, shift);
+}
+
+static int patch_offsets(hpss_batch* b, int W, int shift, const std::vector<int64_t>** host, const int64_t** dev) {
+    std::lock_guard<std::mutex> lk(b->mu);
+    auto key = std::make_pair(W, shift);
+    auto it = b->patch_offs.find(key);
+    if (it == b->patch_offs.end()) {
+        std::vector<int64_t> off(b->n_clips + 1, 0);
+        for (int c = 0; c < b->n_clips; ++c)
+            off[c + 1] = off[c] + hpss_num_patches_tiled(b->frame_off[c + 1] - b->frame_off[c], W, shift);
+        int64_t* d = nullptr;
+        HPSS_CUDA(cudaMalloc(&d, sizeof(int64_t) * off.size()));
+        HPSS_CUDA(cudaMemcpy(d, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice));
+        it = b->patch_offs.emplace(key, std::make_pair(std::move(off), d)).first;
+    }
+    *host = &it->second.first;
+    *dev = it->second.second;
+    return HPSS_OK;
+}
+
+int hpss_patch_offsets(const hpss_batch* batch, int32_t W, int32_t shift, int64_t* out) {
+    if (!batch || !out || W < 1 || shift < 1) { set_error("patch_offsets: bad argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(batch->ctx->device));
+    const std::vector<int64_t>* h; const int64_t* d;
+    int rc = patch_offsets(const_cast<hpss_batch*>(batch), W, shift, &h, &d);
+    if (rc) return rc;
+    memcpy(out, h->data(), sizeof(int64_t) * h->size());
+    return HPSS_OK;
+}
+
+int hpss_patch_tensor(hpss_ctx* ctx, const hpss_batch* batch, float* feat, int32_t D, int32_t standardize, int32_t row0,
+                      int32_t n_rows, int32_t W, int32_t shift, int32_t time_major, int32_t out_f64, void* out,
+                      void* stream) {
+    if (!ctx || !batch || !feat || !out) { set_error("patch_tensor: NULL argument"); return HPSS_ERR_INVALID; }
+    if (D < 1 || row0 < 0 || n_rows < 1 || row0 + n_rows > D || W < 1 || shift < 1) { set_error("patch_tensor: bad shape arguments"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const std::vector<int64_t>* h; const int64_t* d;
+    int rc = patch_offsets(const_cast<hpss_batch*>(batch), W, shift, &h, &d);
+    if (rc) return rc;
+    if (standardize) {
+        rc = launch_row_standardize(ctx, batch, feat, D, st);
+        if (rc) return rc;
+    }
+    return launch_patch_tensor(batch, feat, d, h->back(), D, row0, n_rows, W, shift, time_major, out_f64, out, st);
+}
+
+int hpss_row_nonfinite(hpss_ctx* ctx, const hpss_batch* batch, const float* feat, int32_t D, uint8_t* flags, void* stream) {
+    if (!ctx || !batch || !feat || !flags || D < 1) { set_error("row_nonfinite: bad argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return launch_row_nonfinite(ctx, batch, feat, D, flags, (cudaStream_t)stream);
+}
+
+int hpss_patch_statistics(hpss_ctx* ctx, const double* patches, int64_t n_patches, int32_t n_feat, int32_t n_frames,
+                          int32_t stat, int32_t axis, double* out, void* stream) {
+    if (!ctx || !patches || !out || n_patches < 0 || n_feat < 1 || n_frames < 1) { set_error("patch_statistics: bad argument"); return HPSS_ERR_INVALID; }
+    if (stat < 0 || stat > 3 || (axis != 0 && axis != 1)) { set_error("patch_statistics: stat in 0..3 (mean, variance, skew, kurtosis), axis 0 or 1"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return launch_patch_stats(ctx, patches, n_patches, n_feat, n_frames, stat, axis == 0 ? 1 : 0, out, (cudaStream_t)stream);
 }
 
 int hpss_extract_patches(hpss_ctx* ctx, const float* feat, int32_t D, int64_t T, int32_t W, int32_t shift,

@@ -87,6 +87,18 @@ struct hpss_ctx {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     int max_smem_optin = 0;
     int sm_count = hpss::kSMs;
+    // signal-preparation scratch (prep.cu): descriptors, chunk partials, per-frame gate arrays
+    void* prep_ws = nullptr;
+    size_t prep_ws_bytes = 0;
+    // Every entry point that touches the context's scratch (ws, prep_ws, band_scratch, pipe slots) holds ws_mu
+    // while it enqueues, makes its stream wait for ws_done first and records ws_done when it is through: calls
+    // from different streams or threads are serialised on the device instead of overwriting each other's S / harm /
+    // perc (see hpss::ScratchLease).
+    std::mutex ws_mu;
+    cudaEvent_t ws_done = nullptr;
+    // device status word: bit 0 non-finite audio, bit 1 negative spectrogram input; read by hpss_ctx_check
+    uint32_t* d_flags = nullptr;
+    uint32_t* h_flags = nullptr;      // pinned mirror
 };
 
 struct hpss_batch {
@@ -106,13 +118,38 @@ struct hpss_batch {
     int stft_tt = 0;
     int n_stft_tiles = 0;
     int2* d_stft_tiles = nullptr;
-    int32_t* d_clip_class = nullptr;   // scratch for hpss_moments
+    int32_t* d_clip_class = nullptr;   // class per clip for the moment kernels (kept across calls: re-uploaded only
+    std::vector<int32_t> h_clip_class; //   when the caller passes different classes)
+    std::mutex mu;                     // guards the lazily built members below
+    struct hpss_pipeline* host_pipe = nullptr;   // cached pipeline of hpss_featuregram_host
+    // patch offsets per (patch_size, patch_shift) for hpss_patch_tensor: host prefix + device copy
+    std::map<std::pair<int, int>, std::pair<std::vector<int64_t>, int64_t*>> patch_offs;
     // K2h tile lists of ragged batches, one per (rows, tile length): the (line block, first position) pairs that
     // actually exist (a grid over the longest clip would be mostly empty for MUSAN-shaped length distributions)
     std::map<std::pair<int, int>, std::pair<int2*, int64_t>> time_tiles;
-    // clip chunks of the pipelined host entry (built on first use, owned by this batch)
-    std::vector<int> host_cut;
-    std::vector<hpss_batch*> host_chunks;
+};
+
+// Host-buffer pipeline (api.cu): clip chunks, their sub-batches and the double-buffered device slots
+struct hpss_pipeline {
+    hpss_ctx* ctx = nullptr;
+    hpss_params prm{};
+    int n_clips = 0;
+    int pcm_format = 0;
+    int prepare = 0, fs = 16000;
+    double alpha = 0.025, beta = 0.075;
+    int rows_out = 0;
+    std::vector<int64_t> in_len, in_off;       // raw input samples per clip / prefix
+    std::vector<int64_t> wav_len;              // samples per clip the STFT sees (after the preparation)
+    std::vector<int64_t> frame_off;            // prefix of STFT frames
+    std::vector<int> cut;                      // chunk i = clips [cut[i], cut[i+1])
+    std::vector<hpss_batch*> subs;
+    size_t in_bytes = 0, wav_bytes = 0, out_bytes = 0;    // per-slot capacities (largest chunk)
+    void* slot[2] = {nullptr, nullptr};
+    double* d_acc = nullptr;                   // device moment accumulator
+    double* h_acc = nullptr;                   // pinned mirror
+    int acc_n = 0, acc_classes = 0;
+    int32_t* d_class = nullptr;                // class of every clip of the pipeline
+    size_t ws_need = 0;
 };
 
 namespace hpss {
@@ -121,6 +158,39 @@ int get_fft_plan(hpss_ctx* ctx, int n_fft, int win, FftPlan** out);
 bool stft_fast_split(int n_fft, int* na, int* nb);      // the NA x NB split of the specialised kernel, if any
 int get_mel_plan(hpss_ctx* ctx, int sr, int n_fft, int n_mels, MelPlan** out);
 int ensure_workspace(hpss_ctx* ctx, size_t bytes);
+
+// Serialises the users of the context scratch across streams (see hpss_ctx::ws_done).
+struct ScratchLease {
+    hpss_ctx* ctx = nullptr;
+    cudaStream_t st = nullptr;
+    std::unique_lock<std::mutex> lk;
+    int begin(hpss_ctx* c, cudaStream_t s) {
+        lk = std::unique_lock<std::mutex>(c->ws_mu);
+        ctx = c; st = s;
+        cudaError_t e = cudaStreamWaitEvent(s, c->ws_done, 0);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent(ws_done)");
+        return HPSS_OK;
+    }
+    ~ScratchLease() { if (ctx) cudaEventRecord(ctx->ws_done, st); }
+};
+
+// environment knobs (development only), read once per process
+struct Knobs {
+    int no_sweep, host_chunks, no_uniform_moments, mom_ctas, no_fast_stft, no_uniform_stft, k1_real, sweep1, sweep_u,
+        dct_grid_mult, no_dense_median;
+};
+const Knobs& knobs();
+
+// signal preparation (prep.cu)
+int64_t prep_out_length(int64_t n, int fs);
+int64_t prep_num_frames(int64_t n, int win, int hop);
+int launch_prep(hpss_ctx* ctx, const void* pcm, int pcm_format, const int64_t* clip_len, int n_clips, int fs, int win,
+                int hop, double alpha, double beta, float* out, int32_t* frame_marker, uint8_t* sample_marker,
+                int32_t* n_sil, cudaStream_t st);
+// mode 0: non-finite -> status bit 0; mode 1: negative -> status bit 1 (read by hpss_ctx_check)
+int launch_check(hpss_ctx* ctx, const float* x, int64_t n, int mode, cudaStream_t st);
+int launch_mix(hpss_ctx* ctx, const float* sp, const int64_t* sp_len, const float* mu, const int64_t* mu_len,
+               const double* target_db, int n_pairs, float* out, cudaStream_t st);
 int ensure_stft_tiles(hpss_batch* b, int tt);
 
 // host-side table builders (double precision)
@@ -138,16 +208,7 @@ int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const fl
                     const float* perc, int rows, const float* mel, const int2* band, const int4* sweep,
                     const uint32_t* emit4, const float2* sweep_w, int n_mels, int pre_square, int log_power,
                     float amin, float* out, uint32_t* clip_max, cudaStream_t st);
-int launch_median_freq_fused(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, int rows, int k,
-                             const MelPlan* mel, int log_power, float amin, float* out, uint32_t* clip_max,
-                             cudaStream_t st, bool* handled);
 int launch_median_freq_walk(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, int k, float* out,
-                            cudaStream_t st, bool* handled);
-int launch_perc_mask_mel_walk(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, int rows, int k,
-                              const MelPlan* mel, int log_power, float amin, float* out, uint32_t* clip_max,
-                              cudaStream_t st, bool* handled);
-int launch_perc_mask_mel_ws(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, int rows, int k,
-                            const MelPlan* mel, int log_power, float amin, float* out, uint32_t* clip_max,
                             cudaStream_t st, bool* handled);
 int launch_mel_bands(const float* mel, int n_mels, int rows, int2* band, cudaStream_t st);
 int launch_topdb(hpss_ctx* ctx, const hpss_batch* b, float* out, int rows_per_stream, int n_streams,
@@ -166,6 +227,11 @@ int launch_scale(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, c
 int launch_row_standardize(hpss_ctx* ctx, const hpss_batch* b, float* feat, int D, cudaStream_t st);
 int launch_patches(const float* feat, int D, int64_t T, int W, int shift, int64_t n_patches, double* out,
                    cudaStream_t st);
+int launch_row_nonfinite(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, uint8_t* flags, cudaStream_t st);
+int launch_patch_tensor(const hpss_batch* b, const float* feat, const int64_t* d_patch_off, int64_t n_patches, int D,
+                        int row0, int n_rows, int W, int shift, int time_major, int out_f64, void* out, cudaStream_t st);
+int launch_patch_stats(hpss_ctx* ctx, const double* x, int64_t N, int A, int B, int stat, int along_a, double* out,
+                       cudaStream_t st);
 
 // ---- device helpers ---------------------------------------------------------------
 #ifdef __CUDACC__

@@ -146,7 +146,7 @@ int launch_dct(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int M, int
     const int cols = (n_streams % 2 == 0 && nc4 <= 6) ? 2 : 1;
     const int64_t n_tasks = ((total + 31) / 32) * (n_streams / cols);
     const int64_t want = (n_tasks + kDctWarps - 1) / kDctWarps;
-    static const int mult = [] { const char* e = getenv("HPSS_DCT_GRID_MULT"); return e ? atoi(e) : 8; }();
+    const int mult = knobs().dct_grid_mult;
     const unsigned grid = (unsigned)(mult > 0 ? std::min<int64_t>(want, (int64_t)ctx->sm_count * mult) : want);
 #define HPSS_DCT_LAUNCH(NC4)                                                                                       \
     case NC4: {                                                                                                    \

@@ -406,7 +406,7 @@ int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const fl
     const int ns = hpss_mode ? 2 : 1;
     if (clip_max) HPSS_CUDA(cudaMemsetAsync(clip_max, 0, sizeof(uint32_t) * (size_t)ns * b->n_clips, st));
     if (total == 0) return HPSS_OK;
-    if (hpss_mode && mel && emit4 && sweep_w && (log_power == 0 || log_power == 1) && !getenv("HPSS_SWEEP1")) {
+    if (hpss_mode && mel && emit4 && sweep_w && (log_power == 0 || log_power == 1) && !knobs().sweep1) {
         const int64_t n_warps = (total + 31) / 32;
         const unsigned grid = (unsigned)((n_warps + kWarps - 1) / kWarps);
         if (log_power)
@@ -421,7 +421,7 @@ int launch_mask_mel(hpss_ctx* ctx, const hpss_batch* b, const float* S, const fl
     if (hpss_mode && mel && sweep) {
         const int64_t n_warps = (total + 31) / 32;
         const unsigned grid = (unsigned)((n_warps + kWarps - 1) / kWarps);
-        static const int U = getenv("HPSS_SWEEP_U") ? atoi(getenv("HPSS_SWEEP_U")) : 4;   // development knob
+        const int U = knobs().sweep_u;   // development knob
 #define HPSS_SWEEP_LAUNCH(UU)                                                                                       \
         mask_mel_sweep_kernel<UU><<<grid, kThreads, 0, st>>>(S, harm, perc, b->d_frame_off, b->d_block_clip, total,  \
                                                              rows, sweep, n_mels, log_power, amin, out, clip_max)

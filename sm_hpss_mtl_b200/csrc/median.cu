@@ -18,7 +18,7 @@
 
 #include <algorithm>
 
-#include "maskmath.cuh"
+#include "common.cuh"
 #include "median_networks_gen.cuh"
 
 namespace hpss {
@@ -448,234 +448,6 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
     }
 }
 
-// ---- fused path: frequency median + soft masks + mel sweep + power_to_db (K2p + K3) --------
-// Same tile ring as above, but a compute warp keeps its 32 frames for the whole frequency sweep
-// (all f-tiles in order), so the percussive median never leaves the SM: each lane has S[f] (the
-// centre of its window), perc[f] (the network output) and harm[f] (prefetched from global memory,
-// coalesced across lanes) and forms H = S*mask_h, P = S*mask_p on the spot.  The mel projection is a
-// sweep: the basis is banded with at most two ordered filters overlapping at any f, so two running
-// sums per stream suffice and finished filters are emitted (post_value + coalesced store) as f passes
-// their upper edge -- bit-identical to the stand-alone K3 whole-column path (same f-ascending fmaf
-// order).  The mask / mel / log arithmetic issues on the FMA pipe while the selection network keeps
-// the ALU pipe busy.  Tile order within a round of kComputeWarps items is tile-major, so every compute
-// warp gets its first tile before anyone gets a second one.
-struct FusedArgs {
-    const float* S;
-    const float* harm;
-    float* out;
-    uint32_t* clip_max;      // may be null
-    const int4* sweep;       // null: identity projection ([H; P] rows)
-    int n_mels;
-    int log_power;
-    float amin;
-    int debug;               // development only (HPSS_FUSED_DEBUG): 1 = skip sweep, 2 = skip masks too
-};
-
-constexpr int kFusedLoaderWarps = 4;
-constexpr int kFusedThreads = (kComputeWarps + kFusedLoaderWarps) * 32;
-
-// tile fill for the fused kernel: loader warp lw of kFusedLoaderWarps takes every kFusedLoaderWarps-th position
-__device__ __forceinline__ void fused_tile_fill(uint32_t sm_base, const float* __restrict__ S, const LineInfo& li,
-                                                int lane, int lw, int p0, int halo, int span) {
-    if (li.n <= 0) return;
-    const float* col = S + li.base;
-    const int64_t es = li.estride;
-    const int first = p0 - halo;
-    const int body_lo = max(0, -first);
-    const int body_hi = min(span, li.n - first);
-    constexpr int L = kFusedLoaderWarps;
-    for (int pos = lw; pos < min(body_lo, span); pos += L)
-        cp_async4(sm_base + 4u * (uint32_t)(pos * 32 + lane), col + reflect_idx(first + pos, li.n) * es);
-    {
-        int pos = body_lo + ((lw - body_lo) % L + L) % L;
-        const float* src = col + (int64_t)(first + pos) * es;
-        uint32_t d = sm_base + 4u * (uint32_t)(pos * 32 + lane);
-        const int64_t sstep = es * L;
-#pragma unroll 8
-        for (; pos < body_hi; pos += L, src += sstep, d += 128u * L) cp_async4(d, src);
-    }
-    {
-        int pos = max(body_hi, 0);
-        pos += ((lw - pos) % L + L) % L;
-        for (; pos < span; pos += L)
-            cp_async4(sm_base + 4u * (uint32_t)(pos * 32 + lane), col + reflect_idx(first + pos, li.n) * es);
-    }
-}
-
-template <int K>
-__global__ void __launch_bounds__(kFusedThreads, 1)
-median_freq_fused_kernel(FusedArgs a, const int64_t* __restrict__ frame_off, const int32_t* __restrict__ block_clip,
-                         int rows, int64_t n_lines, int TT, int n_ptiles, int64_t n_blocks, int NB) {
-    constexpr int G = MedianGroup<K>::G;
-    constexpr int HALO = K / 2;
-    extern __shared__ __align__(16) float smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int span = TT + K - 1;
-    const int tile_floats = span * 32;
-    const int NG = TT / G;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NB * tile_floats);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NB);
-    // per-compute-warp scratch for the masked values of one group: [2][G][32] floats
-    float* scr = reinterpret_cast<float*>(bars + 2 * NB) + (size_t)(warp < kComputeWarps ? warp : 0) * (2 * G * 32);
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < NB; ++b) {
-            mbar_init(full0 + 8u * b, 32 * kFusedLoaderWarps);
-            mbar_init(empty0 + 8u * b, 1);
-        }
-    }
-    __syncthreads();
-
-    // items of this CTA: frame blocks blockIdx.x, +gridDim.x, ...; processed in rounds of kComputeWarps
-    const int64_t my_items = (n_blocks > blockIdx.x) ? (n_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t n_rounds = (my_items + kComputeWarps - 1) / kComputeWarps;
-
-    if (warp >= kComputeWarps) {
-        // ===== loader warps: tiles in (round, f-tile, warp) order =====
-        const int lw = warp - kComputeWarps;
-        int64_t q = 0;
-        for (int64_t r = 0; r < n_rounds; ++r) {
-            const int m = (int)min((int64_t)kComputeWarps, my_items - r * kComputeWarps);
-            // the lines of the round's frame blocks are looked up once, not once per tile
-            LineInfo lis[kComputeWarps];
-#pragma unroll
-            for (int w = 0; w < kComputeWarps; ++w) {
-                const int64_t lb = blockIdx.x + (r * kComputeWarps + w) * (int64_t)gridDim.x;
-                lis[w] = lane_line<false>(frame_off, block_clip, rows, w < m ? n_lines : 0, lb * 32 + lane);
-            }
-            for (int pt = 0; pt < n_ptiles; ++pt) {
-#pragma unroll
-                for (int w = 0; w < kComputeWarps; ++w) {
-                    if (w < m) {
-                        const int b = (int)(q % NB);
-                        const uint32_t use = (uint32_t)(q / NB);
-                        if (use > 0) mbar_wait(empty0 + 8u * b, (use - 1) & 1u);
-                        fused_tile_fill(smem_u32(smem + (size_t)b * tile_floats), a.S, lis[w], lane, lw, pt * TT, HALO,
-                                        span);
-                        cp_async_arrive(full0 + 8u * b);
-                        ++q;
-                    }
-                }
-            }
-        }
-    } else {
-        // ===== compute warps =====
-        const bool project = a.sweep != nullptr;
-        const int M = a.n_mels;
-        int64_t qbase = 0;
-        for (int64_t r = 0; r < n_rounds; ++r) {
-            const int m = (int)min((int64_t)kComputeWarps, my_items - r * kComputeWarps);
-            if (warp < m) {
-                const int64_t lb = blockIdx.x + (r * kComputeWarps + warp) * (int64_t)gridDim.x;
-                const int64_t gf = lb * 32 + lane;
-                const bool valid = gf < n_lines;
-                int clip = 0, T = 1;
-                int64_t in_base = 0, out_base = 0;
-                const int rows_out = 2 * (project ? M : rows);
-                if (valid) {
-                    clip = find_clip_hint(frame_off, block_clip, gf);
-                    const int64_t fo = __ldg(frame_off + clip);
-                    T = (int)(__ldg(frame_off + clip + 1) - fo);
-                    in_base = (int64_t)rows * fo + (gf - fo);
-                    out_base = (int64_t)rows_out * fo + (gf - fo);
-                }
-                const float* hcol = a.harm + in_base;
-                float* ocol = a.out + out_base;
-                float aH = 0.f, aP = 0.f, bH = 0.f, bP = 0.f;     // running sums of filters cur, cur + 1
-                int cur = 0;
-                float vmaxH = -INFINITY, vmaxP = -INFINITY;
-
-                for (int pt = 0; pt < n_ptiles; ++pt) {
-                    const int64_t q = qbase + (int64_t)pt * m + warp;
-                    const int b = (int)(q % NB);
-                    const uint32_t use = (uint32_t)(q / NB);
-                    const float* sm = smem + (size_t)b * tile_floats;
-                    const int p0 = pt * TT;
-                    mbar_wait(full0 + 8u * b, use & 1u);
-                    const int ng = min(NG, (rows - p0 + G - 1) / G);
-                    for (int g = 0; g < ng; ++g) {
-                        const int f0 = p0 + g * G;
-                        float hv[G];
-#pragma unroll
-                        for (int j = 0; j < G; ++j)
-                            hv[j] = (valid && f0 + j < rows) ? __ldg(hcol + (int64_t)(f0 + j) * T) : 0.f;
-                        float x[K + G - 1], o[G];
-#pragma unroll
-                        for (int i = 0; i < K + G - 1; ++i) x[i] = sm[(g * G + i) * 32 + lane];
-                        MedianGroup<K>::run(x, o);
-                        // masks of the whole group first (independent straight-line chains), parked in this
-                        // warp's scratch; the sweep below is a rolled loop so its body exists once in the code
-#pragma unroll
-                        for (int j = 0; j < G; ++j) {
-                            float H, P;
-                            if (a.debug & 2) { H = o[j] + hv[j]; P = x[HALO + j]; }
-                            else softmask_apply(x[HALO + j], hv[j], o[j], H, P);
-                            scr[j * 32 + lane] = H;
-                            scr[(G + j) * 32 + lane] = P;
-                        }
-                        int nj = min(G, rows - f0);
-                        if (a.debug & 1) { nj = 0; vmaxH = fmaxf(vmaxH, scr[lane] + scr[G * 32 + lane]); }
-#pragma unroll 1
-                        for (int j = 0; j < nj; ++j) {
-                            const float H = scr[j * 32 + lane], P = scr[(G + j) * 32 + lane];
-                            const int f = f0 + j;
-                            if (project) {
-                                const int4 e = __ldg(a.sweep + f);
-                                while (cur < e.x) {                    // emit finished filters (warp-uniform)
-                                    const float vH = post_value(aH, a.log_power, a.amin);
-                                    const float vP = post_value(aP, a.log_power, a.amin);
-                                    if (valid) {
-                                        ocol[(int64_t)cur * T] = vH;
-                                        ocol[(int64_t)(M + cur) * T] = vP;
-                                    }
-                                    vmaxH = fmaxf(vmaxH, vH);
-                                    vmaxP = fmaxf(vmaxP, vP);
-                                    aH = bH; aP = bP; bH = 0.f; bP = 0.f;
-                                    ++cur;
-                                }
-                                const float wA = __int_as_float(e.y), wB = __int_as_float(e.z);
-                                aH = fmaf(wA, H, aH);
-                                aP = fmaf(wA, P, aP);
-                                bH = fmaf(wB, H, bH);
-                                bP = fmaf(wB, P, bP);
-                            } else {
-                                const float vH = post_value(H, a.log_power, a.amin);
-                                const float vP = post_value(P, a.log_power, a.amin);
-                                if (valid) {
-                                    ocol[(int64_t)f * T] = vH;
-                                    ocol[(int64_t)(rows + f) * T] = vP;
-                                }
-                                vmaxH = fmaxf(vmaxH, vH);
-                                vmaxP = fmaxf(vmaxP, vP);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty0 + 8u * b);
-                }
-                if (project) {
-                    while (cur < M) {                                  // filters above the last frequency row
-                        const float vH = post_value(aH, a.log_power, a.amin);
-                        const float vP = post_value(aP, a.log_power, a.amin);
-                        if (valid) {
-                            ocol[(int64_t)cur * T] = vH;
-                            ocol[(int64_t)(M + cur) * T] = vP;
-                        }
-                        vmaxH = fmaxf(vmaxH, vH);
-                        vmaxP = fmaxf(vmaxP, vP);
-                        aH = bH; aP = bP; bH = 0.f; bP = 0.f;
-                        ++cur;
-                    }
-                }
-                if (a.clip_max != nullptr) {
-                    publish_max(a.clip_max, 2, 0, valid, clip, vmaxH);
-                    publish_max(a.clip_max, 2, 1, valid, clip, vmaxP);
-                }
-            }
-            qbase += (int64_t)m * n_ptiles;
-        }
-    }
-}
-
 // ---- generic path: any k (even k, k > 63): rank counting, O(k^2) per output ---------
 template <bool TIME_AXIS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -827,71 +599,6 @@ int launch_generic(hpss_ctx* ctx, const float* S, float* out, const int64_t* d_f
     return HPSS_OK;
 }
 
-template <int K>
-int launch_fused(hpss_ctx* ctx, const hpss_batch* b, const FusedArgs& fa, int rows, int64_t n_lines, cudaStream_t st) {
-    constexpr int G = MedianGroup<K>::G;
-    // ring depth the tile size is chosen for (development knob: HPSS_FUSED_NB)
-    int want_nb = kComputeWarps + 2;
-    if (const char* e = getenv("HPSS_FUSED_NB")) want_nb = std::max(kComputeWarps + 2, atoi(e));
-    const size_t per_buf = ((size_t)ctx->max_smem_optin - 512 - (size_t)kComputeWarps * 2 * G * 32 * sizeof(float)) /
-                               want_nb - 16;
-    const int max_span = (int)(per_buf / (32 * sizeof(float))) - 1;
-    int tt_max = (max_span - (K - 1)) / G * G;
-    if (tt_max > 16 * G) tt_max = 16 * G;
-    if (tt_max < G) {
-        set_error("median k=%d does not fit the shared-memory tile ring", K);
-        return HPSS_ERR_UNSUPPORTED;
-    }
-    const int64_t nt0 = (rows + tt_max - 1) / tt_max;
-    int TT = (int)((rows + nt0 - 1) / nt0);
-    TT = (TT + G - 1) / G * G;
-    const int n_ptiles = (rows + TT - 1) / TT;
-    const int64_t n_blocks = (n_lines + 31) / 32;
-    const int span = TT + K - 1;
-    const size_t tile_bytes = (size_t)span * 32 * sizeof(float);
-    const size_t scratch = (size_t)kComputeWarps * 2 * G * 32 * sizeof(float);
-    int NB = (int)(((size_t)ctx->max_smem_optin - 512 - scratch) / (tile_bytes + 16));
-    if (NB > 2 * kComputeWarps) NB = 2 * kComputeWarps;
-    const size_t smem = (size_t)NB * tile_bytes + (size_t)NB * 16 + scratch;
-    auto kern = median_freq_fused_kernel<K>;
-    HPSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t grid = (n_blocks + kComputeWarps - 1) / kComputeWarps;
-    if (grid > ctx->sm_count) grid = ctx->sm_count;
-    kern<<<(unsigned)grid, kFusedThreads, smem, st>>>(fa, b->d_frame_off, b->d_block_clip, rows, n_lines, TT, n_ptiles,
-                                                      n_blocks, NB);
-    HPSS_LAUNCHED("median_freq_fused_kernel");
-    return HPSS_OK;
-}
-
-}  // namespace
-
-// K2p + K3 fused.  *handled = false (and nothing launched) when k has no generated network or the mel basis
-// cannot be swept; the caller then runs the separate kernels.
-int launch_median_freq_fused(hpss_ctx* ctx, const hpss_batch* b, const float* S, const float* harm, int rows, int k,
-                             const MelPlan* mel, int log_power, float amin, float* out, uint32_t* clip_max,
-                             cudaStream_t st, bool* handled) {
-    *handled = false;
-    if (mel && !mel->sweepable) return HPSS_OK;
-    const int64_t total_frames = b->frame_off[b->n_clips];
-    FusedArgs fa;
-    fa.S = S; fa.harm = harm; fa.out = out; fa.clip_max = clip_max;
-    fa.sweep = mel ? mel->d_sweep : nullptr;
-    fa.n_mels = mel ? mel->n_mels : 0;
-    fa.log_power = log_power; fa.amin = amin;
-    fa.debug = getenv("HPSS_FUSED_DEBUG") ? atoi(getenv("HPSS_FUSED_DEBUG")) : 0;
-#define HPSS_DISPATCH_FUSED(KK)                                                                   \
-    if (k == KK) {                                                                                \
-        if (clip_max) HPSS_CUDA(cudaMemsetAsync(clip_max, 0, sizeof(uint32_t) * 2 * (size_t)b->n_clips, st)); \
-        *handled = true;                                                                          \
-        if (total_frames == 0) return HPSS_OK;                                                    \
-        return launch_fused<KK>(ctx, b, fa, rows, total_frames, st);                              \
-    }
-    HPSS_MEDIAN_FAST_KS(HPSS_DISPATCH_FUSED)
-#undef HPSS_DISPATCH_FUSED
-    return HPSS_OK;
-}
-
-namespace {
 }  // namespace
 
 int launch_median(hpss_ctx* ctx, const hpss_batch* b, const float* S, int rows, int k, bool time_axis, float* out,

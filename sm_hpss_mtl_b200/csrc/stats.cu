@@ -341,7 +341,149 @@ patches_kernel(const float* __restrict__ feat, int D, int64_t T, int W, int shif
     }
 }
 
+// flags[c * D + d] = 1 when row d of clip c holds a non-finite value (get_data_stats drops such rows per file,
+// lib/preprocessing.py:507-508); one warp per (clip, row) line
+__global__ void __launch_bounds__(kThreads)
+row_nonfinite_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_off, int n_clips, int D,
+                     uint8_t* __restrict__ flags) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_lines = (int64_t)n_clips * D;
+    for (int64_t line = (int64_t)blockIdx.x * kWarps + warp; line < n_lines; line += (int64_t)gridDim.x * kWarps) {
+        const int c = (int)(line / D);
+        const int d = (int)(line - (int64_t)c * D);
+        const int64_t fo = __ldg(frame_off + c);
+        const int T = (int)(__ldg(frame_off + c + 1) - fo);
+        const float* x = feat + (int64_t)D * fo + (int64_t)d * T;
+        bool bad = false;
+        for (int t = lane; t < T; t += 32) bad |= !isfinite(__ldg(x + t));
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) flags[line] = bad ? 1 : 0;
+    }
+}
+
+// N1: model-ready patch tensor.  Patch p of clip c covers frames [p*shift, p*shift + W) of the clip tiled along time
+// until it is longer than W (lib/preprocessing.py:139-142: index t mod T_c), rows [row0, row0 + n_rows) of the
+// (D, T_c) featuregram.  out[(patch, r, w)] (CNN layout, lib/proposed_architectures.py:451) or, TIME_MAJOR,
+// out[(patch, w, r)] (the transposed layout the TCNs take, Proposed_Work_Results.py:235-236).  One CTA = one 32 x 32
+// (row, frame) tile of one patch: reads are coalesced along frames, writes along the innermost output axis (through a
+// shared-memory transpose when that is the row axis).
+template <typename OUT, bool TIME_MAJOR>
+__global__ void __launch_bounds__(kThreads)
+patch_tensor_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_off,
+                    const int64_t* __restrict__ patch_off, int n_clips, int D, int row0, int n_rows, int W, int shift,
+                    OUT* __restrict__ out) {
+    __shared__ float tile[32][33];
+    __shared__ int s_clip;
+    const int64_t p = blockIdx.x;                                  // patches on the x axis (no 65535 limit)
+    if (threadIdx.x == 0) s_clip = find_clip(patch_off, n_clips, p);
+    __syncthreads();
+    const int c = s_clip;
+    const int64_t fo = __ldg(frame_off + c);
+    const int T = (int)(__ldg(frame_off + c + 1) - fo);
+    const int64_t start = (p - __ldg(patch_off + c)) * shift;
+    const float* base = feat + (int64_t)D * fo + (int64_t)row0 * T;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
+    const int w0 = blockIdx.z * 32, r0 = blockIdx.y * 32;
+    OUT* op = out + (int64_t)p * n_rows * W;
+    const int w = w0 + tx;
+    const int t = w < W ? (int)((start + w) % T) : 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i;
+        float v = 0.f;
+        if (r < n_rows && w < W) v = __ldg(base + (int64_t)r * T + t);
+        if (TIME_MAJOR) tile[ty + 8 * i][tx] = v;
+        else if (r < n_rows && w < W) op[(int64_t)r * W + w] = (OUT)v;
+    }
+    if (TIME_MAJOR) {
+        __syncthreads();
+        const int r = r0 + tx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ww = w0 + ty + 8 * i;
+            if (r < n_rows && ww < W) op[(int64_t)ww * n_rows + r] = (OUT)tile[tx][ty + 8 * i];
+        }
+    }
+}
+
+// get_data_statistics (lib/cython_impl/tools.pyx:169-211): per patch, mean / variance (ddof = 0) / scipy.stats.skew /
+// scipy.stats.kurtosis (biased, Fisher) along one axis of a (N, A, B) float64 array.  ALONG_A: reduce over A ->
+// (N, B) (the reference's axis=0, "percussive"); else reduce over B -> (N, A) (axis=1, "harmonic").  One warp per
+// output value, two passes (mean, then central moments) like numpy / scipy.
+template <bool ALONG_A>
+__global__ void __launch_bounds__(kThreads)
+patch_stats_kernel(const double* __restrict__ x, int64_t N, int A, int B, int stat, double* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_red = ALONG_A ? A : B, n_keep = ALONG_A ? B : A;
+    const int64_t total = N * n_keep;
+    for (int64_t o = (int64_t)blockIdx.x * kWarps + warp; o < total; o += (int64_t)gridDim.x * kWarps) {
+        const int64_t n = o / n_keep;
+        const int j = (int)(o - n * n_keep);
+        const double* p = x + n * (int64_t)A * B + (ALONG_A ? j : (int64_t)j * B);
+        const int64_t stride = ALONG_A ? B : 1;
+        double s = 0.0;
+        for (int i = lane; i < n_red; i += 32) s += p[(int64_t)i * stride];
+        const double mean = warp_sum(s) / (double)n_red;
+        double m2 = 0.0, m3 = 0.0, m4 = 0.0;
+        for (int i = lane; i < n_red; i += 32) {
+            const double d = p[(int64_t)i * stride] - mean, d2 = d * d;
+            m2 += d2; m3 += d2 * d; m4 += d2 * d2;
+        }
+        m2 = warp_sum(m2) / (double)n_red;
+        m3 = warp_sum(m3) / (double)n_red;
+        m4 = warp_sum(m4) / (double)n_red;
+        if (lane == 0) {
+            // scipy: NaN where the variance is lost to rounding (m2 <= (eps * mean)^2)
+            const double eps = 2.220446049250313e-16;
+            const bool zero = m2 <= (eps * mean) * (eps * mean);
+            double r;
+            if (stat == 0) r = mean;
+            else if (stat == 1) r = m2;
+            else if (stat == 2) r = zero ? nan("") : m3 / (m2 * sqrt(m2));
+            else r = zero ? nan("") : m4 / (m2 * m2) - 3.0;
+            out[o] = r;
+        }
+    }
+}
+
 }  // namespace
+
+int launch_row_nonfinite(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, uint8_t* flags, cudaStream_t st) {
+    const int64_t n_lines = (int64_t)b->n_clips * D;
+    if (n_lines == 0) return HPSS_OK;
+    int64_t grid = (n_lines + kWarps - 1) / kWarps;
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    row_nonfinite_kernel<<<(unsigned)grid, kThreads, 0, st>>>(feat, b->d_frame_off, b->n_clips, D, flags);
+    HPSS_LAUNCHED("row_nonfinite_kernel");
+    return HPSS_OK;
+}
+
+int launch_patch_tensor(const hpss_batch* b, const float* feat, const int64_t* d_patch_off, int64_t n_patches, int D,
+                        int row0, int n_rows, int W, int shift, int time_major, int out_f64, void* out, cudaStream_t st) {
+    if (n_patches == 0) return HPSS_OK;
+    if (n_patches > 0x7fffffffLL) { set_error("patch_tensor: too many patches"); return HPSS_ERR_UNSUPPORTED; }
+    dim3 grid((unsigned)n_patches, (unsigned)((n_rows + 31) / 32), (unsigned)((W + 31) / 32));
+#define HPSS_PT(OUT, TM) patch_tensor_kernel<OUT, TM><<<grid, kThreads, 0, st>>>(feat, b->d_frame_off, d_patch_off, b->n_clips, D, row0, n_rows, W, shift, (OUT*)out)
+    if (out_f64) { if (time_major) HPSS_PT(double, true); else HPSS_PT(double, false); }
+    else { if (time_major) HPSS_PT(float, true); else HPSS_PT(float, false); }
+#undef HPSS_PT
+    HPSS_LAUNCHED("patch_tensor_kernel");
+    return HPSS_OK;
+}
+
+int launch_patch_stats(hpss_ctx* ctx, const double* x, int64_t N, int A, int B, int stat, int along_a, double* out,
+                       cudaStream_t st) {
+    const int64_t total = N * (along_a ? B : A);
+    if (total == 0) return HPSS_OK;
+    int64_t grid = (total + kWarps - 1) / kWarps;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (grid > cap) grid = cap;
+    if (along_a) patch_stats_kernel<true><<<(unsigned)grid, kThreads, 0, st>>>(x, N, A, B, stat, out);
+    else patch_stats_kernel<false><<<(unsigned)grid, kThreads, 0, st>>>(x, N, A, B, stat, out);
+    HPSS_LAUNCHED("patch_stats_kernel");
+    return HPSS_OK;
+}
 
 static int launch_moments_impl(hpss_ctx* ctx, const hpss_batch* b, float* feat, int D, const int32_t* d_class,
                                int n_classes, double* sum, double* sumsq, double* count, double* nonfinite,
@@ -353,11 +495,11 @@ static int launch_moments_impl(hpss_ctx* ctx, const hpss_batch* b, float* feat, 
         set_error("moments: at most 8 classes are supported (got %d)", n_classes);
         return HPSS_ERR_UNSUPPORTED;
     }
-    if (b->uniform_frames > 0 && b->uniform_frames <= 128 && !getenv("HPSS_NO_UNIFORM_MOMENTS")) {
+    if (b->uniform_frames > 0 && b->uniform_frames <= 128 && !knobs().no_uniform_moments) {
         // equal short clips: constant strides, no per-clip table lookups (moments_uniform_kernel)
         const int T = (int)b->uniform_frames;
         const int rg = (D + kWarps - 1) / kWarps;
-        static const int ctas_per_sm = [] { const char* e = getenv("HPSS_MOM_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 16; }();
+        const int ctas_per_sm = knobs().mom_ctas;
         int want = (ctx->sm_count * ctas_per_sm + rg - 1) / rg;      // ~16 CTAs per SM in total (48: 0.110 ms, 16: 0.103 ms, 8: 0.107 ms on configs[1])
         int per = (b->n_clips + want - 1) / want;
         per = std::max(8, (per + 3) / 4 * 4);

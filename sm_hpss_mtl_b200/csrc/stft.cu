@@ -286,7 +286,7 @@ int choose_stft_tt(const hpss_ctx* ctx, const hpss_batch* b, int n_fft, int hop)
 int launch_stft(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* plan, int hop, int power,
                 float* S, float* cplx, cudaStream_t st) {
     {   // specialised two-pass register FFT for the reference's (n_fft, hop) pairs
-        static const bool no_fast = getenv("HPSS_NO_FAST_STFT") != nullptr;   // development knob
+        const bool no_fast = knobs().no_fast_stft != 0;   // development knob
         bool handled = false;
         if (!no_fast) {
             const int rc = launch_stft_fast(ctx, b, wave, plan, hop, power, S, cplx, st, &handled);

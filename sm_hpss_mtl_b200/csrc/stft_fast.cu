@@ -400,7 +400,7 @@ int launch_r400(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* 
     UniformBatch uni{0, 0, 0, 0};
     const int64_t L = b->uniform_samples;
     if (L > 0 && L % 160 == 0 && b->uniform_frames > 0 && (int64_t)b->n_clips * (L / 160) + 16 < 0x7fffffff &&
-        !getenv("HPSS_NO_UNIFORM_STFT")) {
+        !knobs().no_uniform_stft) {
         uni.fpc = (int)(L / 160);
         uni.T = (int)b->uniform_frames;
         uni.n_clips = b->n_clips;
@@ -438,7 +438,7 @@ int launch_cfg(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftPlan* p
     HPSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
     UniformBatch uni{0, 0, 0, 0};
     const int64_t L = b->uniform_samples;
-    if (L > 0 && L % HOP == 0 && b->uniform_frames > 0 && (int64_t)b->n_clips * (L / HOP) + C::TT < 0x7fffffff && !getenv("HPSS_NO_UNIFORM_STFT")) {
+    if (L > 0 && L % HOP == 0 && b->uniform_frames > 0 && (int64_t)b->n_clips * (L / HOP) + C::TT < 0x7fffffff && !knobs().no_uniform_stft) {
         // equal clips, length a multiple of the hop: 16 consecutive virtual frames per tile, across clip borders
         uni.fpc = (int)(L / HOP);
         uni.T = (int)b->uniform_frames;
@@ -484,7 +484,7 @@ int launch_stft_fast(hpss_ctx* ctx, hpss_batch* b, const float* wave, const FftP
                      float* cplx, cudaStream_t st, bool* handled) {
     *handled = true;
     const int n = plan->n_fft;
-    static const bool use_r400 = [] { const char* e = getenv("HPSS_K1_REAL"); return !e || atoi(e) != 0; }();
+    const bool use_r400 = knobs().k1_real != 0;
     if (n == 400 && hop == 160 && !power && !cplx && use_r400 && plan->d_win_r400) return launch_r400(ctx, b, wave, plan, S, st);
     if (n == 400 && hop == 160) return launch_cfg<400, 160, 10, 20, 10 * HPSS_K1_TT400>(ctx, b, wave, plan, power, S, cplx, st);
     if (n == 512 && hop == 160) return launch_cfg<512, 160, 16, 16, 256>(ctx, b, wave, plan, power, S, cplx, st);

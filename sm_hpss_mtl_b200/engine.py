@@ -209,19 +209,6 @@ def mask_mel_log(batch: Batch, S: torch.Tensor, harm: Optional[torch.Tensor], pe
     return out, clip_max
 
 
-def perc_mask_mel_log(batch: Batch, S: torch.Tensor, harm: torch.Tensor, rows: int, k: int, mel_sr: int = 22050,
-                      n_mels: int = 0, log_power: int = 0, amin: float = 1e-10):
-    """K2p + K3 fused (frequency median + masks + mel + log); returns (out, clip_max or None)."""
-    rows_out = 2 * (n_mels if n_mels > 0 else rows)
-    out = torch.empty(rows_out * batch.total_frames, dtype=torch.float32, device=S.device)
-    clip_max = torch.empty(2 * max(1, batch.n_clips), dtype=torch.int32, device=S.device) if log_power else None
-    check(batch.lib.hpss_perc_mask_mel_log(batch.ctx.handle, batch.handle, _dev_ptr(S, torch.float32, "S"),
-                                           _dev_ptr(harm, torch.float32, "harm"), int(rows), int(k), int(mel_sr),
-                                           int(n_mels), int(log_power), float(amin), _dev_ptr(out), _dev_ptr(clip_max),
-                                           _stream_ptr()))
-    return out, clip_max
-
-
 def topdb_clip(batch: Batch, out: torch.Tensor, rows_per_stream: int, n_streams: int, clip_max: torch.Tensor,
                top_db: float = 80.0) -> torch.Tensor:
     if top_db < 0:
@@ -270,15 +257,153 @@ def featuregram_from_spec(batch: Batch, S: torch.Tensor, rows: int, params: Para
     return out
 
 
-def host_alloc(n_floats: int) -> np.ndarray:
-    """float32 numpy array over pinned host memory owned by the library (freed with the array)."""
+def host_alloc(n: int, dtype=np.float32) -> np.ndarray:
+    """numpy array (float32 by default) over pinned host memory owned by the library (freed with the array)."""
     lib = _lib.load()
+    dt = np.dtype(dtype)
     p = C.c_void_p()
-    check(lib.hpss_host_alloc(C.byref(p), int(n_floats) * 4))
-    buf = (C.c_float * int(n_floats)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=np.float32)
+    check(lib.hpss_host_alloc(C.byref(p), int(n) * dt.itemsize))
+    buf = (C.c_byte * (int(n) * dt.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt)
     weakref.finalize(arr, lib.hpss_host_free, C.c_void_p(p.value))    # views keep `arr` alive via .base
     return arr
+
+
+def ctx_check(ctx: Context) -> None:
+    """Synchronise the current stream and raise what the kernels flagged since the last check
+    (ParameterError for non-finite audio / negative spectrogram input, as librosa does)."""
+    check(ctx.lib.hpss_ctx_check(ctx.handle, _stream_ptr()))
+
+
+def validate_audio(ctx: Context, wave: torch.Tensor) -> None:
+    """librosa.util.valid_audio as a device pass; the verdict arrives with the next ctx_check."""
+    check(ctx.lib.hpss_validate_audio(ctx.handle, _dev_ptr(wave, torch.float32, "wave"), int(wave.numel()), _stream_ptr()))
+
+
+def validate_nonneg(ctx: Context, x: torch.Tensor) -> None:
+    """softmask's "X and X_ref must be non-negative" as a device pass (verdict with the next ctx_check)."""
+    check(ctx.lib.hpss_validate_nonneg(ctx.handle, _dev_ptr(x, torch.float32, "x"), int(x.numel()), _stream_ptr()))
+
+
+# ---------------------------------------------------------------------------- N2: signal preparation
+def prep_out_length(n_samples: int, fs: int = 16000) -> int:
+    return int(_lib.load().hpss_prep_out_length(int(n_samples), int(fs)))
+
+
+def prep_num_frames(n_samples: int, win_length: int, hop_length: int) -> int:
+    return int(_lib.load().hpss_prep_num_frames(int(n_samples), int(win_length), int(hop_length)))
+
+
+def prep_signals(ctx: Context, pcm: torch.Tensor, clip_lengths: Sequence[int], fs: int = 16000, win_length: int = 400,
+                 hop_length: int = 160, alpha: float = 0.025, beta: float = 0.075, markers: bool = False):
+    """load_and_preprocess_signal after the decode (normalise, RMS gate, silence excision, doubling of clips
+    shorter than 0.1 s, normalise) for a batch of files on the device.
+
+    pcm: CUDA float32 or int16 tensor holding the files back to back.  Returns the prepared float32 signals back to
+    back (clip c has prep_out_length(len_c) samples); with ``markers`` also (frame_marker int32, sample_marker uint8,
+    n_sil int32) -- the reference's frame_silMarker / sample_silMarker and the number of qualifying stretches."""
+    lens = np.ascontiguousarray(clip_lengths, dtype=np.int64)
+    if pcm.dtype == torch.float32:
+        fmt = _lib.PCM_F32
+    elif pcm.dtype == torch.int16:
+        fmt = _lib.PCM_S16
+    else:
+        raise ValueError(f"pcm must be float32 or int16, got {pcm.dtype}")
+    if int(lens.sum()) != pcm.numel():
+        raise ValueError(f"pcm has {pcm.numel()} samples, clip_lengths sum to {int(lens.sum())}")
+    out_len = [prep_out_length(int(n), fs) for n in lens]
+    out = torch.empty(int(sum(out_len)), dtype=torch.float32, device=pcm.device)
+    fm = sm = ns = None
+    if markers:
+        nfr = sum(prep_num_frames(int(n), win_length, hop_length) for n in lens)
+        fm = torch.zeros(nfr, dtype=torch.int32, device=pcm.device)
+        sm = torch.zeros(pcm.numel(), dtype=torch.uint8, device=pcm.device)
+        ns = torch.zeros(max(1, lens.size), dtype=torch.int32, device=pcm.device)
+    check(ctx.lib.hpss_prep_signals(ctx.handle, _dev_ptr(pcm, None, "pcm"), fmt, lens.ctypes.data_as(C.POINTER(C.c_int64)),
+                                    int(lens.size), int(fs), int(win_length), int(hop_length), float(alpha), float(beta),
+                                    _dev_ptr(out), _dev_ptr(fm), _dev_ptr(sm), _dev_ptr(ns), _stream_ptr()))
+    if markers:
+        return out, out_len, fm, sm, ns
+    return out, out_len
+
+
+def mix_signals(ctx: Context, sp: torch.Tensor, sp_lengths: Sequence[int], mu: torch.Tensor, mu_lengths: Sequence[int],
+                target_db: Sequence[float]) -> torch.Tensor:
+    """mix_signals (lib/preprocessing.py:297-325) for pairs of prepared signals on the device."""
+    sl = np.ascontiguousarray(sp_lengths, dtype=np.int64)
+    ml = np.ascontiguousarray(mu_lengths, dtype=np.int64)
+    db = np.ascontiguousarray(target_db, dtype=np.float64)
+    if not (sl.size == ml.size == db.size):
+        raise ValueError("one speech length, music length and target ratio per pair")
+    if int(sl.sum()) != sp.numel() or int(ml.sum()) != mu.numel():
+        raise ValueError("signal buffers do not match the given lengths")
+    out = torch.empty(sp.numel(), dtype=torch.float32, device=sp.device)
+    check(ctx.lib.hpss_mix_signals(ctx.handle, _dev_ptr(sp, torch.float32, "sp"), sl.ctypes.data_as(C.POINTER(C.c_int64)),
+                                   _dev_ptr(mu, torch.float32, "mu"), ml.ctypes.data_as(C.POINTER(C.c_int64)),
+                                   C.c_void_p(db.ctypes.data), int(sl.size), _dev_ptr(out), _stream_ptr()))
+    return out
+
+
+class Pipeline:
+    """Host-buffer pipeline (hpss_pipeline_*): decoded files or prepared waveforms in host memory -> features in
+    host memory and / or the raw moments of get_data_stats, H2D / kernels / D2H overlapped over clip chunks."""
+
+    def __init__(self, ctx: Context, clip_lengths: Sequence[int], params: Params, pcm_dtype=np.float32,
+                 prepare: bool = False, fs: int = 16000, alpha: float = 0.025, beta: float = 0.075, n_chunks: int = 0):
+        self.ctx, self.lib, self.params = ctx, ctx.lib, params
+        self.pcm_dtype = np.dtype(pcm_dtype)
+        fmt = {np.dtype(np.float32): _lib.PCM_F32, np.dtype(np.int16): _lib.PCM_S16}[self.pcm_dtype]
+        lens = np.ascontiguousarray(clip_lengths, dtype=np.int64)
+        h = C.c_void_p()
+        check(self.lib.hpss_pipeline_create(ctx.handle, lens.ctypes.data_as(C.POINTER(C.c_int64)), int(lens.size),
+                                            C.byref(params), fmt, int(bool(prepare)), int(fs), float(alpha), float(beta),
+                                            int(n_chunks), C.byref(h)))
+        self.handle = h
+        self.n_clips = int(lens.size)
+        self.total_samples = int(lens.sum())
+        self.total_frames = int(self.lib.hpss_pipeline_total_frames(h))
+        self.n_chunks = int(self.lib.hpss_pipeline_n_chunks(h))
+        self.rows = feature_rows(params)
+        fo = np.zeros(self.n_clips + 1, dtype=np.int64)
+        check(self.lib.hpss_pipeline_frame_offsets(h, fo.ctypes.data_as(C.POINTER(C.c_int64))))
+        self.frame_offsets = fo
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.hpss_pipeline_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, pcm_host: np.ndarray, feat_host: Optional[np.ndarray] = None, clip_class: Optional[Sequence[int]] = None,
+            n_classes: int = 0, moments: Optional[np.ndarray] = None, want_features: bool = True):
+        """Returns (feat_host or None, moments or None).  ``moments`` (float64, moments layout of :func:`moments`)
+        is accumulated into when given, created zeroed when ``clip_class`` is given without it."""
+        if pcm_host.dtype != self.pcm_dtype or not pcm_host.flags.c_contiguous or pcm_host.size != self.total_samples:
+            raise ValueError(f"pcm_host must be C-contiguous {self.pcm_dtype} with {self.total_samples} samples")
+        if want_features and feat_host is None:
+            feat_host = np.empty(self.rows * self.total_frames, dtype=np.float32)
+        if feat_host is not None and (feat_host.dtype != np.float32 or feat_host.size != self.rows * self.total_frames):
+            raise ValueError("feat_host has the wrong dtype/size")
+        cls = None
+        if clip_class is not None:
+            cls = np.ascontiguousarray(clip_class, dtype=np.int32)
+            if cls.size != self.n_clips:
+                raise ValueError("clip_class must have one entry per clip")
+            n = n_classes * self.rows + self.rows + n_classes + 1
+            if moments is None:
+                moments = np.zeros(n, dtype=np.float64)
+            if moments.dtype != np.float64 or moments.size != n or not moments.flags.c_contiguous:
+                raise ValueError(f"moments must be a contiguous float64 array of {n} entries")
+        check(self.lib.hpss_pipeline_run(self.handle, C.c_void_p(pcm_host.ctypes.data),
+                                         C.c_void_p(feat_host.ctypes.data) if feat_host is not None else C.c_void_p(0),
+                                         C.c_void_p(cls.ctypes.data) if cls is not None else C.c_void_p(0),
+                                         int(n_classes), C.c_void_p(moments.ctypes.data) if cls is not None else C.c_void_p(0)))
+        return feat_host, moments
 
 
 def featuregram_host(batch: Batch, wave_host: np.ndarray, params: Params, out_host: Optional[np.ndarray] = None):
@@ -309,7 +434,7 @@ def moments(batch: Batch, feat: torch.Tensor, D: int, clip_class: Sequence[int],
         raise ValueError("clip_class must have one entry per clip")
     base = acc.data_ptr()
     check(batch.lib.hpss_moments(batch.ctx.handle, batch.handle, _dev_ptr(feat, torch.float32, "feat"), int(D),
-                                 C.c_void_p(cls.ctypes.data), int(n_classes), C.c_void_p(base),
+                                 C.c_void_p(cls.ctypes.data), int(cls.size), int(n_classes), C.c_void_p(base),
                                  C.c_void_p(base + 8 * n_classes * D), C.c_void_p(base + 8 * (n_classes * D + D)),
                                  C.c_void_p(base + 8 * (n_classes * D + D + n_classes)), _stream_ptr()))
     return acc
@@ -322,10 +447,12 @@ def topdb_moments(batch: Batch, out: torch.Tensor, rows_per_stream: int, n_strea
     if acc is None:
         acc = torch.zeros(n_classes * D + D + n_classes + 1, dtype=torch.float64, device=out.device)
     cls = np.ascontiguousarray(clip_class, dtype=np.int32)
+    if cls.size != batch.n_clips:
+        raise ValueError("clip_class must have one entry per clip")
     base = acc.data_ptr()
     check(batch.lib.hpss_topdb_moments(batch.ctx.handle, batch.handle, _dev_ptr(out, torch.float32, "out"),
                                        int(rows_per_stream), int(n_streams), _dev_ptr(clip_max), float(top_db),
-                                       C.c_void_p(cls.ctypes.data), int(n_classes), C.c_void_p(base),
+                                       C.c_void_p(cls.ctypes.data), int(cls.size), int(n_classes), C.c_void_p(base),
                                        C.c_void_p(base + 8 * n_classes * D), C.c_void_p(base + 8 * (n_classes * D + D)),
                                        C.c_void_p(base + 8 * (n_classes * D + D + n_classes)), _stream_ptr()))
     return acc
@@ -348,7 +475,7 @@ def featuregram_moments(batch: Batch, wave: torch.Tensor, params: Params, clip_c
     base = acc.data_ptr()
     check(batch.lib.hpss_featuregram_moments(batch.ctx.handle, batch.handle, _dev_ptr(wave, torch.float32, "wave"),
                                              C.byref(params), _dev_ptr(out, torch.float32, "out"),
-                                             C.c_void_p(cls.ctypes.data), int(n_classes), C.c_void_p(base),
+                                             C.c_void_p(cls.ctypes.data), int(cls.size), int(n_classes), C.c_void_p(base),
                                              C.c_void_p(base + 8 * n_classes * D),
                                              C.c_void_p(base + 8 * (n_classes * D + D)),
                                              C.c_void_p(base + 8 * (n_classes * D + D + n_classes)), _stream_ptr()))
@@ -393,4 +520,57 @@ def extract_patches(ctx: Context, feat: torch.Tensor, patch_size: int, patch_shi
     if n:
         check(ctx.lib.hpss_extract_patches(ctx.handle, _dev_ptr(feat, torch.float32, "feat"), D, T, int(patch_size),
                                            int(patch_shift), _dev_ptr(out), _stream_ptr()))
+    return out
+
+
+def num_patches_tiled(n_frames: int, patch_size: int, patch_shift: int) -> int:
+    return int(_lib.load().hpss_num_patches_tiled(int(n_frames), int(patch_size), int(patch_shift)))
+
+
+def patch_offsets(batch: Batch, patch_size: int, patch_shift: int) -> np.ndarray:
+    out = np.zeros(batch.n_clips + 1, dtype=np.int64)
+    check(batch.lib.hpss_patch_offsets(batch.handle, int(patch_size), int(patch_shift),
+                                       out.ctypes.data_as(C.POINTER(C.c_int64))))
+    return out
+
+
+def patch_tensor(batch: Batch, feat: torch.Tensor, D: int, patch_size: int, patch_shift: int, standardize: bool = True,
+                 rows: str = "all", time_major: bool = False, dtype=torch.float32) -> torch.Tensor:
+    """N1 on the device: featuregrams of a batch -> the model-ready patch tensor (n_patches, n_rows, W), or
+    (n_patches, W, n_rows) with ``time_major`` (the TCN layout).  ``rows``: "all" | "harm" | "perc".
+    ``standardize`` applies the per-file StandardScaler IN PLACE on ``feat`` first.  The result is a torch CUDA tensor
+    (hand it on with torch.utils.dlpack.to_dlpack / __dlpack__)."""
+    half = D // 2
+    row0, n_rows = {"all": (0, D), "harm": (0, half), "perc": (half, D - half)}[rows]
+    off = patch_offsets(batch, patch_size, patch_shift)
+    n = int(off[-1])
+    shape = (n, patch_size, n_rows) if time_major else (n, n_rows, patch_size)
+    if dtype not in (torch.float32, torch.float64):
+        raise ValueError("dtype must be torch.float32 or torch.float64")
+    out = torch.empty(shape, dtype=dtype, device=feat.device)
+    check(batch.lib.hpss_patch_tensor(batch.ctx.handle, batch.handle, _dev_ptr(feat, torch.float32, "feat"), int(D),
+                                      int(bool(standardize)), int(row0), int(n_rows), int(patch_size), int(patch_shift),
+                                      int(bool(time_major)), int(dtype == torch.float64), _dev_ptr(out), _stream_ptr()))
+    return out
+
+
+def row_nonfinite(batch: Batch, feat: torch.Tensor, D: int) -> torch.Tensor:
+    flags = torch.empty(max(1, batch.n_clips * D), dtype=torch.uint8, device=feat.device)
+    check(batch.lib.hpss_row_nonfinite(batch.ctx.handle, batch.handle, _dev_ptr(feat, torch.float32, "feat"), int(D),
+                                       _dev_ptr(flags), _stream_ptr()))
+    return flags[:batch.n_clips * D].view(batch.n_clips, D)
+
+
+STATS = {"mean": 0, "variance": 1, "skew": 2, "kurtosis": 3}
+
+
+def patch_statistics(ctx: Context, patches: torch.Tensor, stat_type: str = "skew", axis: int = 0) -> torch.Tensor:
+    """get_data_statistics (tools.pyx:169-211) on the device: patches (N, f, t) float64 -> (N, t) for axis=0,
+    (N, f) for axis=1."""
+    if patches.dim() != 3:
+        raise ValueError("patches must be (N, nFeat, nFrames)")
+    N, A, B = (int(x) for x in patches.shape)
+    out = torch.empty((N, B if axis == 0 else A), dtype=torch.float64, device=patches.device)
+    check(ctx.lib.hpss_patch_statistics(ctx.handle, _dev_ptr(patches, torch.float64, "patches"), N, A, B,
+                                        STATS[stat_type], int(axis), _dev_ptr(out), _stream_ptr()))
     return out

@@ -39,12 +39,12 @@ def stft(y, n_fft=2048, hop_length=None, win_length=None, center=False):
         raise ParameterError("Audio data must be floating-point")
     if y.ndim != 1:
         raise ParameterError("only mono input is supported")
-    if not np.isfinite(y).all():
-        raise ParameterError("Audio buffer is not finite everywhere")
     ctx = _ctx()
     batch = engine.Batch(ctx, clip_lengths=[y.shape[0]], n_fft=n_fft, hop_length=hop_length)   # raises if n_fft > len(y)
     wave = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).cuda()
+    engine.validate_audio(ctx, wave)                       # librosa.util.valid_audio, on the device
     _, cplx = engine.stft_mag(batch, wave, n_fft, win_length, hop_length, return_complex=True)
+    engine.ctx_check(ctx)                                  # raises ParameterError("Audio buffer is not finite everywhere")
     out = cplx.cpu().numpy().reshape(1 + n_fft // 2, -1)
     batch.close()
     return out
@@ -66,15 +66,15 @@ def hpss(S, kernel_size=31, power=2.0, mask=False, margin=1.0):
         raise ParameterError("Margins must be >= 1.0. A typical range is between 1 and 10.")
     if power != 2.0 or mh != 1.0 or mp != 1.0 or mask:
         raise NotImplementedError("only power=2.0, margin=1.0, mask=False (librosa's defaults, used by the reference)")
-    if np.any(S < 0):
-        raise ParameterError("X and X_ref must be non-negative")
     rows, T = S.shape
     ctx = _ctx()
     batch = engine.Batch(ctx, clip_frames=[T])
     Sd = torch.from_numpy(np.ascontiguousarray(S, dtype=np.float32).ravel()).cuda()
-    harm = engine.median_time(batch, Sd, rows, int(win_harm))
+    engine.validate_nonneg(ctx, Sd)                        # softmask's input check, on the device (medians of
+    harm = engine.median_time(batch, Sd, rows, int(win_harm))   # non-negative data are non-negative)
     perc = engine.median_freq(batch, Sd, rows, int(win_perc))
     out, _ = engine.mask_mel_log(batch, Sd, harm, perc, rows)
+    engine.ctx_check(ctx)                                  # raises ParameterError("X and X_ref must be non-negative")
     res = out.cpu().numpy().reshape(2 * rows, T)
     batch.close()
     return res[:rows].copy(), res[rows:].copy()

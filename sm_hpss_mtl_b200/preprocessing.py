@@ -4,9 +4,9 @@ Same function names, argument meaning, return layout and dtypes as
 /root/reference/lib/preprocessing.py (get_featuregram :355, get_feature_patches :137,
 get_data_stats :461, scale_data :590) and lib/cython_impl/tools.pyx (scale_data :138,
 extract_patches :21).  All feature arithmetic (STFT, HPSS medians, soft masks, mel, power_to_db,
-row standardisation, patch gather, moments) runs in libhpss_b200.so on the GPU; there is no CPU
-fallback.  What stays on the host is file I/O, the ``.npy`` feature cache and the signal
-preparation that precedes the hot path (normalise / silence removal / SMR mixing).
+row standardisation, patch gather, moments) and the signal preparation in front of it (normalise, RMS gate,
+silence removal, SMR mixing: SURVEY.md row N2) run in libhpss_b200.so on the GPU; there is no CPU
+fallback.  What stays on the host is decoding files, the ``.npy`` feature cache and the statistics pickle.
 """
 from __future__ import annotations
 
@@ -64,33 +64,68 @@ def make_params(PARAMS, fs, n_fft, n_mels, featName):
                               n_mels=max(int(n_mels), 1), mel_sr=int(fs) if mel_uses_fs else 22050, feature=fam)
 
 
+# ============================================================================ host staging
+_PINNED = {}
+
+
+def _pinned(n: int, dtype, slot: str) -> np.ndarray:
+    """Grow-only pinned staging buffers (one per role), so H2D / D2H run at link rate without per-call
+    cudaHostAlloc."""
+    from . import engine
+    dt = np.dtype(dtype)
+    key = (slot, dt.str)
+    buf = _PINNED.get(key)
+    if buf is None or buf.size < n:
+        buf = _PINNED[key] = engine.host_alloc(max(int(n * 1.25), 1 << 16), dt)
+    return buf[:n]
+
+
+_PIPES = {}
+
+
+def _pipeline(ctx, lengths, prm, pcm_dtype, prepare, fs=FS):
+    """Small cache of host pipelines keyed by (clip lengths, parameters): repeated calls with the same shapes
+    (mini-batches of equal segments, benchmark loops) reuse chunk layouts and device slots."""
+    from . import engine
+    key = (ctx.device, tuple(int(x) for x in lengths), bytes(prm), np.dtype(pcm_dtype).str, bool(prepare), int(fs))
+    pl = _PIPES.get(key)
+    if pl is None:
+        if len(_PIPES) >= 8:
+            _PIPES.pop(next(iter(_PIPES))).close()
+        pl = _PIPES[key] = engine.Pipeline(ctx, lengths, prm, pcm_dtype=pcm_dtype, prepare=prepare, fs=fs)
+    return pl
+
+
 # ============================================================================ GPU feature extraction
 def featuregram_batch(signals: Sequence[np.ndarray], fs: int, PARAMS, n_fft: int, n_mels: int, featName: str,
                       device: Optional[int] = None) -> List[np.ndarray]:
-    """Featuregrams of many already-prepared signals in one batched GPU call.
+    """Featuregrams of many already-prepared signals in one batched GPU call (pinned staging, H2D / kernels /
+    D2H pipelined by hpss_pipeline_run).
 
     Returns one float32 (nFeat, T_c) array per signal, exactly what get_featuregram returns per file."""
-    import torch
     from . import engine
-    sigs = [np.ascontiguousarray(x, dtype=np.float32) for x in signals]
+    sigs = [np.asarray(x) for x in signals]
     for x in sigs:
         if x.ndim != 1:
             raise ParameterError("only mono input is on the reference path")
-        if not np.isfinite(x).all():
-            raise ParameterError("Audio buffer is not finite everywhere")      # librosa.util.valid_audio
+    if not sigs:
+        return []
     ctx = engine.get_context(device)
     prm = make_params(PARAMS, fs, n_fft, n_mels, featName)
-    batch = engine.Batch(ctx, clip_lengths=[len(x) for x in sigs], n_fft=n_fft, hop_length=prm.hop_length)
-    rows = engine.feature_rows(prm)
-    with torch.cuda.device(ctx.device):
-        wave = torch.from_numpy(np.concatenate(sigs) if sigs else np.zeros(0, np.float32)).cuda()
-        out = engine.featuregram(batch, wave, prm)
-        host = out.cpu().numpy()
+    lengths = [len(x) for x in sigs]
+    pl = _pipeline(ctx, lengths, prm, np.float32, False)
+    wave = _pinned(sum(lengths), np.float32, "wave")
+    o = 0
+    for x in sigs:
+        wave[o:o + len(x)] = x                                           # float64 mixes are rounded here, once
+        o += len(x)
+    rows = pl.rows
+    out = _pinned(rows * pl.total_frames, np.float32, "feat")
+    pl.run(wave, feat_host=out)                                          # raises ParameterError on non-finite audio
     res = []
-    for c in range(batch.n_clips):
-        a, b = rows * int(batch.frame_offsets[c]), rows * int(batch.frame_offsets[c + 1])
-        res.append(host[a:b].reshape(rows, -1).copy())
-    batch.close()
+    for c in range(pl.n_clips):
+        a, b = rows * int(pl.frame_offsets[c]), rows * int(pl.frame_offsets[c + 1])
+        res.append(out[a:b].reshape(rows, -1).copy())
     return res
 
 
@@ -104,8 +139,6 @@ def featuregram_from_spec(Spec: np.ndarray, PARAMS, n_mels: int, featName: str) 
     import torch
     from . import engine
     Spec = np.ascontiguousarray(Spec, dtype=np.float32)
-    if (Spec < 0).any():
-        raise ParameterError("X and X_ref must be non-negative")             # librosa.util.softmask
     rows, T = Spec.shape
     if featName == 'LogMelSpec':
         fam, sr = 'LOGMELSPEC', 22050     # melspectrogram(S=Spec): default sr; S is used as is (no squaring)
@@ -124,102 +157,98 @@ def featuregram_from_spec(Spec: np.ndarray, PARAMS, n_mels: int, featName: str) 
         engine.topdb_clip(batch, out, n_mels, 1, cmax, 80.0)
         res = out.cpu().numpy().reshape(n_mels, T)
     else:
-        res = engine.featuregram_from_spec(batch, S, rows, prm).cpu().numpy().reshape(2 * n_mels, T)
+        out = engine.featuregram_from_spec(batch, S, rows, prm)         # flags negative input (softmask raises)
+        engine.ctx_check(ctx)
+        res = out.cpu().numpy().reshape(2 * n_mels, T)
     batch.close()
     return res
 
 
-# ============================================================================ signal preparation (host)
+# ============================================================================ signal preparation (GPU, row N2)
 def normalize_signal(Xin):
-    """lib/preprocessing.py:114-132."""
+    """lib/preprocessing.py:114-132 (two numpy reductions; the feature path itself normalises on the device)."""
     Xin = Xin - np.mean(Xin)
     Xin = Xin / np.max(np.abs(Xin))
     return Xin
 
 
-def _frame_rms(y: np.ndarray, frame_length: int, hop_length: int) -> np.ndarray:
-    """librosa.feature.rms(y=..., center=True, pad_mode='reflect')[0]."""
-    yp = np.pad(y, int(frame_length // 2), mode='reflect')
-    n = 1 + (len(yp) - frame_length) // hop_length
-    # sliding sum of squares via a cumulative sum would change rounding; frame explicitly like librosa
-    idx = np.arange(frame_length)[:, None] + hop_length * np.arange(n)[None, :]
-    x = yp[idx]
-    return np.sqrt(np.mean(np.abs(x) ** 2, axis=0))
+def _as_pcm(x) -> np.ndarray:
+    """Decoded audio as the device accepts it: int16 PCM stays int16 (half the upload; librosa's x / 32768 is
+    applied on the device), everything else becomes float32."""
+    x = np.asarray(x)
+    if x.ndim != 1:
+        raise ParameterError("only mono input is on the reference path")
+    if x.dtype != np.int16:
+        x = x.astype(np.float32, copy=False)
+    return np.ascontiguousarray(x)
 
 
-def removeSilence(Xin, nSamples, energy, nFrames, fs, Tw, Ts, alpha=0.025, beta=0.075):
-    """Silence excision with the semantics of the reference's Cython leaf
-    (lib/cython_impl/tools.pyx:42-134), including its quirks: the energy threshold is a float32,
-    nothing is removed unless MORE than one silent stretch qualifies, and the returned signal keeps
-    its original length -- the kept samples are packed to the front of a float32 buffer of ones."""
-    from scipy.signal import medfilt
-    frameSize = int((Tw * fs) / 1000)
-    frameShift = int((Ts * fs) / 1000)
-    thresh = np.float32(alpha * np.max(energy))
-    marker = (np.asarray(energy) >= thresh).astype(np.float64)
-    marker = (medfilt(marker, 5) > 0.5).astype(np.int64)
-    sample_marker = np.ones(nSamples, dtype=np.int64)
-    total, nSil, i = 0, 0, 0
-    last = nFrames - 1
-    while i < nFrames:
-        # i: first silent frame at/after i (or the last frame); j: first active frame after it (or the last)
-        nz = np.flatnonzero(marker[i:] == 0)
-        i = i + int(nz[0]) if nz.size else last
-        nz = np.flatnonzero(marker[i:] == 1)
-        j = i + int(nz[0]) if nz.size else last
-        k = max(frameShift * (i - 1) + frameSize, 1)
-        l = min(frameShift * (j - 1) + frameSize, nSamples)
-        if (l - k) / fs > beta:
-            sample_marker[k:l] = 0
-            nSil += 1
-            total += int((l - k) / fs)          # the reference accumulates into a C int
-        i = j + 1
-    if nSil > 1:
-        keep = np.flatnonzero(sample_marker == 1)
-        out = np.ones(nSamples, dtype=np.float32)
-        out[:keep.size] = Xin[keep]
-    else:
-        out = Xin
-    return out, sample_marker, marker, total
+def prepare_signals_device(ctx, pcms: Sequence[np.ndarray], Tw, Ts, fs: int = FS, markers: bool = False):
+    """load_and_preprocess_signal after the decode for a list of files, on the device (engine.prep_signals).
+    Returns (flat CUDA float32 tensor, per-file output lengths[, frame markers, sample markers, n_sil])."""
+    import torch
+    from . import engine
+    pcms = [_as_pcm(x) for x in pcms]
+    if len({x.dtype for x in pcms}) > 1:
+        pcms = [x.astype(np.float32) / np.float32(32768.0) if x.dtype == np.int16 else x for x in pcms]
+    lengths = [len(x) for x in pcms]
+    host = _pinned(sum(lengths), pcms[0].dtype, "pcm")
+    o = 0
+    for x in pcms:
+        host[o:o + len(x)] = x
+        o += len(x)
+    with torch.cuda.device(ctx.device):
+        dev = torch.from_numpy(host).cuda(non_blocking=True)
+        res = engine.prep_signals(ctx, dev, lengths, fs=fs, win_length=int((Tw * fs) / 1000),
+                                  hop_length=int((Ts * fs) / 1000), markers=markers)
+        # the pinned buffer may be reused by the next call: the upload has to be through
+        torch.cuda.current_stream().synchronize()
+    return res
+
+
+def load_and_preprocess_signal(fName, Tw, Ts, loader=None):
+    """lib/preprocessing.py:330-350: decode on the host, everything else (normalise, RMS gate, silence removal with the
+    Cython leaf's semantics, doubling below 0.1 s, normalise) on the GPU."""
+    from . import engine
+    Xin = (loader or load_pcm)(fName)
+    ctx = engine.get_context()
+    out, _ = prepare_signals_device(ctx, [Xin], Tw, Ts)
+    engine.ctx_check(ctx)
+    return out.cpu().numpy(), FS
 
 
 def mix_signals(Xin_sp, Xin_mu, target_dB):
-    """lib/preprocessing.py:297-325: loop the music up to the speech length, scale it to the target
-    speech-to-music ratio, weight both so the factors sum to one, normalise."""
-    n_sp = len(Xin_sp)
-    reps = int(np.ceil(n_sp / len(Xin_mu))) if len(Xin_mu) < n_sp else 1
-    mu = np.tile(Xin_mu, reps) if reps > 1 else Xin_mu.copy()
-    common = min(n_sp, len(mu))
-    sp, mu = Xin_sp[:common], mu[:common]
-    e_sp = np.sum(np.power(sp, 2)) / len(sp)
-    e_mu = np.sum(np.power(mu, 2)) / len(mu)
-    g_mu = np.sqrt((e_sp / np.power(10, (target_dB / 10))) / e_mu)
-    g_sp = 1
-    tot = g_mu + g_sp
-    g_mu /= tot
-    g_sp /= tot
-    return normalize_signal(g_sp * sp + g_mu * mu)
+    """lib/preprocessing.py:297-325 on the GPU (hpss_mix_signals): the music is looped up to the speech length and
+    scaled to the target speech-to-music ratio, both weights divided by their sum, the mix normalised."""
+    import torch
+    from . import engine
+    ctx = engine.get_context()
+    sp = torch.from_numpy(np.ascontiguousarray(Xin_sp, dtype=np.float32)).cuda()
+    mu = torch.from_numpy(np.ascontiguousarray(Xin_mu, dtype=np.float32)).cuda()
+    return engine.mix_signals(ctx, sp, [sp.numel()], mu, [mu.numel()], [float(target_dB)]).cpu().numpy()
 
 
-def load_audio(fName: str, sr: int = FS) -> np.ndarray:
-    """Mono float32 audio at ``sr`` (stand-in for librosa.core.load(fName, mono=True, sr=16000)).
-    Reads RIFF/WAVE PCM (scipy.io.wavfile) and ``.npy`` waveforms; MUSAN is 16 kHz wav, which
-    librosa returns as int16 / 32768.  Other sample rates are resampled with scipy's polyphase
-    filter, which is NOT bit-identical to librosa's resampy kernel."""
+def load_pcm(fName: str, sr: int = FS) -> np.ndarray:
+    """Decode one file to mono samples at ``sr``: int16 for 16-bit PCM wav at the right rate (MUSAN), float32
+    otherwise (stand-in for librosa.core.load(fName, mono=True, sr=16000); ``.npy`` waveforms are accepted too).
+    Other sample rates are resampled with scipy's polyphase filter, which is NOT bit-identical to librosa's
+    resampy kernel."""
     if fName.endswith('.npy'):
         x = np.load(fName)
         rate = sr
     else:
         from scipy.io import wavfile
         rate, x = wavfile.read(fName)
-        if x.dtype == np.int16:
-            x = x.astype(np.float32) / 32768.0
-        elif x.dtype == np.int32:
-            x = x.astype(np.float32) / 2147483648.0
-        elif x.dtype == np.uint8:
-            x = (x.astype(np.float32) - 128.0) / 128.0
-        else:
-            x = x.astype(np.float32)
+    if x.dtype == np.int16 and x.ndim == 1 and rate == sr:
+        return np.ascontiguousarray(x)
+    if x.dtype == np.int16:
+        x = x.astype(np.float32) / 32768.0
+    elif x.dtype == np.int32:
+        x = x.astype(np.float32) / 2147483648.0
+    elif x.dtype == np.uint8:
+        x = (x.astype(np.float32) - 128.0) / 128.0
+    else:
+        x = x.astype(np.float32)
     if x.ndim > 1:
         x = np.mean(x, axis=1 if x.shape[1] < x.shape[0] else 0)
     if rate != sr:
@@ -230,57 +259,96 @@ def load_audio(fName: str, sr: int = FS) -> np.ndarray:
     return np.ascontiguousarray(x, dtype=np.float32)
 
 
-def load_and_preprocess_signal(fName, Tw, Ts, loader=load_audio):
-    """lib/preprocessing.py:330-350."""
-    Xin = loader(fName)
-    fs = FS
-    Xin = normalize_signal(Xin)
-    frameSize = int((Tw * fs) / 1000)
-    frameShift = int((Ts * fs) / 1000)
-    energy = _frame_rms(Xin, frameSize, frameShift)
-    Xin_silrem, _, _, _ = removeSilence(Xin, len(Xin), energy, len(energy), fs, Tw, Ts)
-    Xin = Xin_silrem.copy()
-    if len(Xin) / fs < 0.1:
-        while len(Xin) / fs < 0.1:
-            Xin = np.append(Xin, Xin)
-    return normalize_signal(Xin), fs
+def load_audio(fName: str, sr: int = FS) -> np.ndarray:
+    """Mono float32 audio at ``sr`` (what librosa.core.load returns)."""
+    x = load_pcm(fName, sr)
+    if x.dtype == np.int16:
+        x = x.astype(np.float32) / np.float32(32768.0)
+    return x
 
 
 # ============================================================================ get_featuregram
-def _feature_name_of_file(fName_path_sp, fName_path_mu, target_dB):
+def _stem_of(path):
+    return path.split('/')[-1].split('.')[0]
+
+
+def _feature_name_of_file(fName_path_sp, fName_path_mu, target_dB, fName_path_no=''):
+    """Cache-file stem: lib/preprocessing.py:356-361; with the noise path, 5_class_classification.py:315-324."""
     if (fName_path_sp != '') and (fName_path_mu != ''):
-        return (fName_path_sp.split('/')[-1].split('.')[0] + '_' + fName_path_mu.split('/')[-1].split('.')[0]
-                + '_' + str(target_dB) + 'dB')
+        return _stem_of(fName_path_sp) + '_' + _stem_of(fName_path_mu) + '_' + str(target_dB) + 'dB'
+    if (fName_path_sp != '') and (fName_path_no != ''):
+        return _stem_of(fName_path_sp) + '_' + _stem_of(fName_path_no) + '_' + str(target_dB) + 'dB'
     if fName_path_sp != '':
-        return fName_path_sp.split('/')[-1].split('.')[0]
+        return _stem_of(fName_path_sp)
     if fName_path_mu != '':
-        return fName_path_mu.split('/')[-1].split('.')[0]
-    raise ValueError("both file names are empty")
+        return _stem_of(fName_path_mu)
+    if fName_path_no != '':
+        return _stem_of(fName_path_no)
+    raise ValueError("all file names are empty")
 
 
-def prepare_signal(PARAMS, classname, fName_path_sp, fName_path_mu, target_dB, loader=load_audio):
-    """Signal of one get_featuregram call (lib/preprocessing.py:364-376)."""
+def _sources(classname, fName_path_sp, fName_path_mu, fName_path_no=''):
+    """(first file, second file or None) of a class (lib/preprocessing.py:364-376; 5_class_classification.py:327-349)."""
     if classname == 'speech_music':
-        sp, fs = load_and_preprocess_signal(fName_path_sp, PARAMS['Tw'], PARAMS['Ts'], loader)
-        mu, fs = load_and_preprocess_signal(fName_path_mu, PARAMS['Tw'], PARAMS['Ts'], loader)
-        return mix_signals(sp, mu, target_dB), fs
+        return fName_path_sp, fName_path_mu
+    if classname == 'speech_noise':
+        return fName_path_sp, fName_path_no
     if classname in ('speech', 'muspeak'):
-        return load_and_preprocess_signal(fName_path_sp, PARAMS['Tw'], PARAMS['Ts'], loader)
+        return fName_path_sp, None
     if classname == 'music':
-        return load_and_preprocess_signal(fName_path_mu, PARAMS['Tw'], PARAMS['Ts'], loader)
+        return fName_path_mu, None
+    if classname == 'noise':
+        return fName_path_no, None
     raise ValueError(f"unknown classname {classname!r}")
 
 
-def get_featuregram(PARAMS, classname, feature_opDir, fName_path_sp, fName_path_mu, target_dB, n_fft, n_mels,
-                    featName, save_feat=True, loader=load_audio):
-    """Same signature, cache layout and return value as lib/preprocessing.py:355-457."""
-    fName = _feature_name_of_file(fName_path_sp, fName_path_mu, target_dB)
-    cache = feature_opDir + '/' + classname + '/' + fName + '.npy'
+def prepare_signal_device(ctx, PARAMS, classname, fName_path_sp, fName_path_mu, target_dB, loader=None,
+                          fName_path_no=''):
+    """Prepared (and, for the mixed classes, mixed) signal of one get_featuregram call as a CUDA float32 tensor."""
+    from . import engine
+    loader = loader or load_pcm
+    first, second = _sources(classname, fName_path_sp, fName_path_mu, fName_path_no)
+    pcms = [loader(first)] + ([loader(second)] if second is not None else [])
+    flat, lens = prepare_signals_device(ctx, pcms, PARAMS['Tw'], PARAMS['Ts'])
+    if second is None:
+        return flat
+    return engine.mix_signals(ctx, flat[:lens[0]], [lens[0]], flat[lens[0]:], [lens[1]], [float(target_dB)])
+
+
+def prepare_signal(PARAMS, classname, fName_path_sp, fName_path_mu, target_dB, loader=None, fName_path_no=''):
+    """Signal of one get_featuregram call (lib/preprocessing.py:364-376) as a numpy array."""
+    from . import engine
+    ctx = engine.get_context()
+    x = prepare_signal_device(ctx, PARAMS, classname, fName_path_sp, fName_path_mu, target_dB, loader, fName_path_no)
+    engine.ctx_check(ctx)
+    return x.cpu().numpy(), FS
+
+
+def _featuregram_of_files(PARAMS, classname, fName_path_sp, fName_path_mu, fName_path_no, target_dB, n_fft, n_mels,
+                          featName, loader):
+    """decode (host) -> upload -> prepare [-> mix] -> features, one download of the result."""
+    import torch
+    from . import engine
+    ctx = engine.get_context()
+    with torch.cuda.device(ctx.device):
+        wave = prepare_signal_device(ctx, PARAMS, classname, fName_path_sp, fName_path_mu, target_dB, loader,
+                                     fName_path_no)
+        prm = make_params(PARAMS, FS, n_fft, n_mels, featName)
+        batch = engine.Batch(ctx, clip_lengths=[wave.numel()], n_fft=n_fft, hop_length=prm.hop_length)
+        out = engine.featuregram(batch, wave, prm)
+        rows = engine.feature_rows(prm)
+        host = _pinned(out.numel(), np.float32, "feat1")
+        torch.from_numpy(host).copy_(out, non_blocking=True)
+        engine.ctx_check(ctx)                        # synchronises; raises like librosa on non-finite audio
+        batch.close()
+    return host.reshape(rows, -1).copy()
+
+
+def _cached_featuregram(cache, compute, save_feat):
     if not os.path.exists(cache):
-        Xin, fs = prepare_signal(PARAMS, classname, fName_path_sp, fName_path_mu, target_dB, loader)
-        fv = featuregram_from_signal(Xin, fs, PARAMS, n_fft, n_mels, featName)
+        fv = compute()
         if save_feat:
-            os.makedirs(feature_opDir + '/' + classname + '/', exist_ok=True)
+            os.makedirs(os.path.dirname(cache) + '/', exist_ok=True)
             np.save(cache, fv)
     else:
         try:
@@ -291,6 +359,36 @@ def get_featuregram(PARAMS, classname, feature_opDir, fName_path_sp, fName_path_
     return fv
 
 
+def get_featuregram(PARAMS, classname, feature_opDir, fName_path_sp, fName_path_mu, target_dB, n_fft, n_mels,
+                    featName, save_feat=True, loader=None):
+    """Same signature, cache layout and return value as lib/preprocessing.py:355-457."""
+    fName = _feature_name_of_file(fName_path_sp, fName_path_mu, target_dB)
+    cache = feature_opDir + '/' + classname + '/' + fName + '.npy'
+    return _cached_featuregram(cache, lambda: _featuregram_of_files(
+        PARAMS, classname, fName_path_sp, fName_path_mu, '', target_dB, n_fft, n_mels, featName, loader), save_feat)
+
+
+def get_featuregram_5class(PARAMS, classname, feature_opDir, fName_path_sp, fName_path_mu, fName_path_no, target_dB,
+                           n_fft, n_mels, featName, save_feat=True, loader=None):
+    """The 5-class script's copy of get_featuregram (5_class_classification.py:314-385): one more positional, the
+    noise file; classes 'noise' and 'speech_noise' (speech mixed with noise at target_dB) next to the other three.
+    Only 'LogMelSpec' and the 'LogMelHarm*' / 'LogMelPerc*' names exist there."""
+    if not (featName == 'LogMelSpec' or featName.startswith('LogMelHarm') or featName.startswith('LogMelPerc')):
+        raise ValueError(f"featName {featName!r} is not computed by the 5-class script")
+    fName = _feature_name_of_file(fName_path_sp, fName_path_mu, target_dB, fName_path_no)
+    cache = feature_opDir + '/' + classname + '/' + fName + '.npy'
+    return _cached_featuregram(cache, lambda: _featuregram_of_files(
+        PARAMS, classname, fName_path_sp, fName_path_mu, fName_path_no, target_dB, n_fft, n_mels, featName, loader),
+        save_feat)
+
+
+def get_featuregram_from_spec(PARAMS, feature_opDir, fName, Spec, n_fft, n_mels, featName, save_feat=True):
+    """The long-form script's variant (DAFx12_Speech_Music_Detection_B3_MTL_v2.py:230-255): a precomputed whole-file
+    magnitude spectrogram in, cache file feature_opDir/fName.npy."""
+    cache = feature_opDir + '/' + fName + '.npy'
+    return _cached_featuregram(cache, lambda: featuregram_from_spec(Spec, PARAMS, n_mels, featName), save_feat)
+
+
 # ============================================================================ patches
 def _stem(featName: str) -> str:
     for pre in ('LogMel', 'Mel', 'Log'):
@@ -299,39 +397,64 @@ def _stem(featName: str) -> str:
     return featName
 
 
-def get_feature_patches(PARAMS, FV, patch_size, patch_shift, featName):
-    """lib/preprocessing.py:137-292 on the GPU: per-file StandardScaler of every feature row (unless
-    frame_level_scaling), patch gather -> float64 (nPatch, nFeat, W[, 1]); harmonic/percussive halves
-    selected or stacked on axis 1 by the feature name."""
-    import torch
-    from . import engine
-    FV = np.asarray(FV)
-    if FV.shape[1] < patch_size:                                   # :139-142
-        FV1 = FV.copy()
-        while FV.shape[1] <= patch_size:
-            FV = np.append(FV, FV1, axis=1)
+def _patch_rows(featName: str) -> str:
     plain = featName in ('Spec', 'LogSpec', 'MelSpec', 'LogMelSpec')
     stem = _stem(featName)
     if not plain and stem not in ('HarmSpec', 'PercSpec', 'HarmPercSpec'):
         raise ValueError(f"unknown featName {featName!r}")
-    half = int(FV.shape[0] / 2)
     if plain or stem == 'HarmPercSpec':
-        block = FV                       # row standardisation is per row: both halves at once
-    elif stem == 'HarmSpec':
-        block = FV[:half]
-    else:
-        block = FV[half:]
+        return "all"                      # row standardisation is per row: both halves at once
+    return "harm" if stem == 'HarmSpec' else "perc"
+
+
+def feature_patches_device(PARAMS, batch, feat, D, patch_size, patch_shift, featName, time_major=None, dtype=None):
+    """Row N1, device resident: featuregrams of a whole batch (``feat``: CUDA float32 in the batch layout, e.g. the
+    output of engine.featuregram) -> the model-ready patch tensor on the device.  Per-file StandardScaler (unless
+    frame_level_scaling; in place on ``feat``), tiling of clips shorter than the patch, patch gather, H/P selection
+    by the feature name; the TCN models ('Lemaire_et_al' in the model name) get (n, W, nFeat) -- the transpose of
+    Proposed_Work_Results.py:235-236 -- the CNNs (n, nFeat, W, 1).  float32 by default (what the network consumes)."""
+    import torch
+    from . import engine
+    tcn = 'Lemaire_et_al' in PARAMS['Model']
+    tm = tcn if time_major is None else bool(time_major)
+    out = engine.patch_tensor(batch, feat, D, patch_size, patch_shift, standardize=not PARAMS['frame_level_scaling'],
+                              rows=_patch_rows(featName), time_major=tm, dtype=dtype or torch.float32)
+    return out if tcn else out.unsqueeze(3)
+
+
+def get_feature_patches(PARAMS, FV, patch_size, patch_shift, featName):
+    """lib/preprocessing.py:137-292 on the GPU: per-file StandardScaler of every feature row (unless
+    frame_level_scaling), patch gather -> float64 (nPatch, nFeat, W[, 1]); harmonic/percussive halves
+    selected or stacked on axis 1 by the feature name.  (Compatibility wrapper: numpy in, float64 numpy out; the
+    device-resident form is feature_patches_device.)"""
+    import torch
+    from . import engine
+    FV = np.asarray(FV)
+    rows = _patch_rows(featName)
     ctx = engine.get_context()
-    D, T = block.shape
-    feat = torch.from_numpy(np.ascontiguousarray(block, dtype=np.float32)).cuda()
-    if not PARAMS['frame_level_scaling']:
-        batch = engine.Batch(ctx, clip_frames=[T])
-        engine.row_standardize(batch, feat.view(-1), D)
-        batch.close()
-    patches = engine.extract_patches(ctx, feat, patch_size, patch_shift).cpu().numpy()
+    D, T = FV.shape
+    feat = torch.from_numpy(np.ascontiguousarray(FV, dtype=np.float32)).cuda()
+    batch = engine.Batch(ctx, clip_frames=[T])
+    patches = engine.patch_tensor(batch, feat.view(-1), D, patch_size, patch_shift,
+                                  standardize=not PARAMS['frame_level_scaling'], rows=rows, time_major=False,
+                                  dtype=torch.float64).cpu().numpy()
+    batch.close()
     if 'Lemaire_et_al' not in PARAMS['Model']:
         patches = np.expand_dims(patches, axis=3)
     return patches
+
+
+def get_data_statistics(FV, stat_type='skew', axis=0):
+    """lib/cython_impl/tools.pyx:169-211 on the GPU: per-patch mean / variance / skew / kurtosis vectors of a
+    (N, f, t) patch array along axis 0 (over f -> (N, t)) or 1 (over t -> (N, f))."""
+    import torch
+    from . import engine
+    FV = np.asarray(FV)
+    if FV.ndim == 4 and FV.shape[3] == 1:
+        FV = FV[:, :, :, 0]                               # np.squeeze of the CNN patches
+    ctx = engine.get_context()
+    x = torch.from_numpy(np.ascontiguousarray(FV, dtype=np.float64)).cuda()
+    return engine.patch_statistics(ctx, x, stat_type, axis).cpu().numpy()
 
 
 # ============================================================================ global statistics
@@ -360,72 +483,231 @@ def _scale(FV, mean, stdev, eps, out_dtype):
     return res.astype(out_dtype, copy=False)
 
 
+class _Moments:
+    """Raw moments of get_data_stats accumulated on the device over many batches of featuregrams, with the
+    reference's per-file dropping of feature rows that hold a NaN / Inf (lib/preprocessing.py:507-508)."""
+
+    def __init__(self, ctx, n_classes, chunk_frames=1 << 20):
+        self.ctx, self.n_classes, self.chunk_frames = ctx, n_classes, chunk_frames
+        self.D = None
+        self.acc = None
+        self.bad_rows = None                  # feature rows dropped (must be the same rows in every file)
+        self.n_files = 0
+        self.pend, self.pend_cls, self.pend_frames = [], [], 0
+
+    def add(self, fv: np.ndarray, cls: int):
+        if self.D is None:
+            self.D = fv.shape[0]
+        self.pend.append(fv)
+        self.pend_cls.append(cls)
+        self.pend_frames += fv.shape[1]
+        if self.pend_frames >= self.chunk_frames:
+            self.flush()
+
+    def add_device(self, batch, feat, D, classes):
+        """Featuregrams already on the device (batch layout)."""
+        from . import engine
+        if self.D is None:
+            self.D = D
+        self.acc = engine.moments(batch, feat, D, classes, self.n_classes, acc=self.acc)
+        self._rows(batch, feat, D)
+
+    def _rows(self, batch, feat, D):
+        from . import engine
+        bad_total = float(self.acc[-1].item())            # synchronises; 8 bytes
+        seen = getattr(self, "_bad_seen", 0.0)
+        if bad_total != seen:                             # this batch holds non-finite values: which rows, which files?
+            flags = engine.row_nonfinite(batch, feat, D).cpu().numpy().astype(bool)
+            for c in range(batch.n_clips):
+                self._merge(flags[c])
+            self._bad_seen = bad_total
+        elif self.bad_rows is not None and self.bad_rows.any():
+            self._merge(np.zeros(D, dtype=bool))          # a clean file after a file with dropped rows
+        self.n_files += batch.n_clips
+
+    def _merge(self, mask):
+        if self.bad_rows is None:
+            if self.n_files > 0 and mask.any():
+                raise ValueError("operands could not be broadcast together: files drop different non-finite "
+                                 "feature rows (lib/preprocessing.py:507-529)")
+            self.bad_rows = mask.copy()
+        elif not np.array_equal(self.bad_rows, mask):
+            raise ValueError("operands could not be broadcast together: files drop different non-finite feature rows "
+                             "(lib/preprocessing.py:507-529)")
+
+    def flush(self):
+        import torch
+        from . import engine
+        if not self.pend:
+            return
+        batch = engine.Batch(self.ctx, clip_frames=[fv.shape[1] for fv in self.pend])
+        n = sum(fv.size for fv in self.pend)
+        host = _pinned(n, np.float32, "statfeat")
+        o = 0
+        for fv in self.pend:
+            host[o:o + fv.size] = np.asarray(fv, dtype=np.float32).ravel()
+            o += fv.size
+        flat = torch.from_numpy(host).cuda(non_blocking=True)
+        self.acc = engine.moments(batch, flat, self.D, self.pend_cls, self.n_classes, acc=self.acc)
+        self._rows(batch, flat, self.D)                   # synchronises: the pinned buffer is free again
+        batch.close()
+        self.pend, self.pend_cls, self.pend_frames = [], [], 0
+
+    def result(self, group=None):
+        import torch
+        from .dist import allreduce_moments, finalize_stats, moments_size
+        self.flush()
+        err = None
+        if self.acc is None:
+            if self.D is None:
+                err = ValueError("no featuregrams given")
+                self.D = 1
+            self.acc = torch.zeros(moments_size(self.D, self.n_classes), dtype=torch.float64, device='cuda')
+        allreduce_moments(self.acc, group)                # every rank reaches the collective before anyone raises
+        if err is not None:
+            raise err
+        host = self.acc.cpu().numpy().copy()
+        host[-1] = 0.0                                    # non-finite values sit in dropped rows only (checked above)
+        mean, std, counts = finalize_stats(host, self.D, self.n_classes)
+        if self.bad_rows is not None and self.bad_rows.any():
+            mean, std = mean[~self.bad_rows], std[~self.bad_rows]
+        return mean, std, [int(c) for c in counts]
+
+
 def data_stats_from_featuregrams(class_to_fvs: Dict[str, List[np.ndarray]], classes: Sequence[str],
                                  group=None, chunk_frames: int = 1 << 20):
     """Global feature mean / stdev of get_data_stats (lib/preprocessing.py:461-586) from featuregrams held
     in memory: raw float64 moments per batch on the GPU, SUM all-reduce over the process group (the only
-    collective on the path), closed-form finish.  Returns (mean f32[D], stdev f32[D], *per-class counts)."""
-    import torch
+    collective on the path; pass featuregrams of THIS rank's files only), closed-form finish.
+    Returns (mean f32[D], stdev f32[D], *per-class counts in the order of ``classes``)."""
     from . import engine
-    from .dist import allreduce_moments, finalize_stats
-    ctx = engine.get_context()
-    n_classes = len(classes)
-    D = None
-    acc = None
-    pend, pend_cls, pend_frames = [], [], 0
-
-    def flush():
-        nonlocal acc, pend, pend_cls, pend_frames
-        if not pend:
-            return
-        batch = engine.Batch(ctx, clip_frames=[fv.shape[1] for fv in pend])
-        flat = torch.from_numpy(np.concatenate([np.ascontiguousarray(fv, dtype=np.float32).ravel() for fv in pend])).cuda()
-        acc = engine.moments(batch, flat, D, pend_cls, n_classes, acc=acc)
-        torch.cuda.synchronize()
-        batch.close()
-        pend, pend_cls, pend_frames = [], [], 0
-
+    m = _Moments(engine.get_context(), len(classes), chunk_frames)
     for k, name in enumerate(classes):
         for fv in class_to_fvs.get(name, []):
-            if D is None:
-                D = fv.shape[0]
-            pend.append(fv)
-            pend_cls.append(k)
-            pend_frames += fv.shape[1]
-            if pend_frames >= chunk_frames:
-                flush()
-    flush()
-    if acc is None:
-        if D is None:
-            raise ValueError("no featuregrams given")
-        acc = torch.zeros(n_classes * D + D + n_classes + 1, dtype=torch.float64, device='cuda')
-    allreduce_moments(acc, group)
-    mean, std, counts = finalize_stats(acc.cpu().numpy(), D, n_classes)
-    return (mean, std, *[int(c) for c in counts])
+            m.add(fv, k)
+    mean, std, counts = m.result(group)
+    return (mean, std, *counts)
 
 
-def get_data_stats(PARAMS, files, loader=load_audio):
-    """Same signature and return value as lib/preprocessing.py:461-586: every file of every class goes
-    through get_featuregram (cached .npy or computed), statistics as in data_stats_from_featuregrams."""
+def _stat_jobs(PARAMS, files):
+    """(class name, speech path, music path, SMR) of every file get_data_stats visits (lib/preprocessing.py:476-504)."""
+    classes = PARAMS['classes']
+    jobs = []
+    for clNum in classes.keys():
+        name = classes[clNum]
+        file_list = files['speech+music'] if name == 'speech_music' else files[name]
+        for fl in file_list:
+            if name == 'speech_music':
+                jobs.append((name, PARAMS['folder'] + '/speech/' + fl['speech'], PARAMS['folder'] + '/music/' + fl['music'],
+                             fl['SMR']))
+            elif name == 'music':
+                jobs.append((name, '', PARAMS['folder'] + '/music/' + fl.split('.')[0] + '.wav', -1))
+            else:
+                jobs.append((name, PARAMS['folder'] + '/' + name + '/' + fl.split('.')[0] + '.wav', '', -1))
+    return jobs
+
+
+def get_data_stats(PARAMS, files, loader=None, group=None, shard=True, batch_samples: int = 1 << 27):
+    """Same signature and return value as lib/preprocessing.py:461-586: (mean f32[D], stdev f32[D], nMuFrames,
+    nSpFrames, nSpMuFrames).  Every file of every class goes through the feature cache (``.npy`` under
+    feature_opDir) or is computed: files without a cache entry are decoded on the host, uploaded as PCM in
+    batches, prepared, featurised and reduced to raw moments on the device by one hpss_pipeline_run per batch (the
+    features come back only to be written to the cache); speech+music mixes go file by file.  Under
+    torch.distributed (``shard``) the job list is cut into one contiguous slice per rank and the moment vector is
+    SUM-all-reduced once, at the end."""
+    import torch
+    from . import engine
     classes = PARAMS['classes']
     folder = PARAMS['feature_opDir']
     model = PARAMS['Model']
     featName, n_fft, n_mels = PARAMS['featName'][model], PARAMS['n_fft'][model], PARAMS['n_mels'][model]
     names = [classes[k] for k in classes.keys()]
-    groups: Dict[str, List[np.ndarray]] = {n: [] for n in names}
-    for name in names:
-        file_list = files['speech+music'] if name == 'speech_music' else files[name]
-        for fl in file_list:
-            if name == 'speech_music':
-                sp = PARAMS['folder'] + '/speech/' + fl['speech']
-                mu = PARAMS['folder'] + '/music/' + fl['music']
-                FV = get_featuregram(PARAMS, 'speech_music', folder, sp, mu, fl['SMR'], n_fft, n_mels, featName,
-                                     loader=loader)
-            elif name == 'music':
-                mu = PARAMS['folder'] + '/music/' + fl.split('.')[0] + '.wav'
-                FV = get_featuregram(PARAMS, 'music', folder, '', mu, -1, n_fft, n_mels, featName, loader=loader)
-            else:
-                sp = PARAMS['folder'] + '/' + name + '/' + fl.split('.')[0] + '.wav'
-                FV = get_featuregram(PARAMS, name, folder, sp, '', -1, n_fft, n_mels, featName, loader=loader)
-            groups[name].append(FV)
-    return data_stats_from_featuregrams(groups, names)
+    jobs = _stat_jobs(PARAMS, files)
+    rank, world = 0, 1
+    try:
+        import torch.distributed as dist
+        if shard and dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+    except Exception:
+        pass
+    if world > 1:
+        per = (len(jobs) + world - 1) // world
+        jobs = jobs[rank * per:(rank + 1) * per]
+    ctx = engine.get_context()
+    mom = _Moments(ctx, len(names))
+    loader = loader or load_pcm
+    prm = make_params(PARAMS, FS, n_fft, n_mels, featName)
+    pend = []                                             # (class index, cache path, pcm) of plain files to compute
+
+    def run_pending():
+        if not pend:
+            return
+        lens = [len(p[2]) for p in pend]
+        dt = np.int16 if all(p[2].dtype == np.int16 for p in pend) else np.float32
+        host = _pinned(sum(lens), dt, "pcm")
+        o = 0
+        for _, _, x in pend:
+            host[o:o + len(x)] = x if x.dtype == dt else x.astype(np.float32) / np.float32(32768.0)
+            o += len(x)
+        pl = engine.Pipeline(ctx, lens, prm, pcm_dtype=dt, prepare=True, fs=FS)
+        feat = _pinned(pl.rows * pl.total_frames, np.float32, "feat")
+        acc = np.zeros(len(names) * pl.rows + pl.rows + len(names) + 1)
+        pl.run(host, feat_host=feat, clip_class=[p[0] for p in pend], n_classes=len(names), moments=acc)
+        if acc[-1] == 0:                                  # the common case: moments straight from the pipeline
+            if mom.D is None:
+                mom.D = pl.rows
+            t = torch.from_numpy(acc).cuda()
+            mom.acc = t if mom.acc is None else mom.acc + t
+            if mom.bad_rows is not None and mom.bad_rows.any():
+                mom._merge(np.zeros(pl.rows, dtype=bool))
+            mom.n_files += len(pend)
+        for c, (k, cache, _) in enumerate(pend):
+            a, b = pl.rows * int(pl.frame_offsets[c]), pl.rows * int(pl.frame_offsets[c + 1])
+            fv = feat[a:b].reshape(pl.rows, -1)
+            os.makedirs(os.path.dirname(cache) + '/', exist_ok=True)
+            np.save(cache, fv)
+            if acc[-1] != 0:                              # non-finite values: the slow path sorts out which rows
+                mom.add(fv.copy(), k)
+        pl.close()
+        pend.clear()
+
+    pend_samples = 0
+    for (name, sp, mu, smr) in jobs:
+        k = names.index(name)
+        cache = folder + '/' + name + '/' + _feature_name_of_file(sp, mu, smr) + '.npy'
+        if os.path.exists(cache) or name == 'speech_music':
+            mom.add(get_featuregram(PARAMS, name, folder, sp, mu, smr, n_fft, n_mels, featName, loader=loader), k)
+        else:
+            x = _as_pcm(loader(sp or mu))
+            pend.append((k, cache, x))
+            pend_samples += len(x)
+            if pend_samples >= batch_samples:
+                run_pending()
+                pend_samples = 0
+    run_pending()
+    mean, std, counts = mom.result(group)
+    by_name = dict(zip(names, counts))
+    return mean, std, by_name.get('music', 0), by_name.get('speech', 0), by_name.get('speech_music', 0)
+
+
+def save_data_stats(PARAMS, fold, mean, stdev, nFrames, split='train'):
+    """The statistics pickle of Baseline_Results.py:609-616 (lib/misc.py:20-22): same file name, keys and protocol."""
+    import pickle
+    name = 'data_stats_fold' + str(fold) + '_' + str(len(PARAMS['classes'])) + 'class_' + split
+    stats = {'mean': mean, 'stdev': stdev, 'nFrames': list(nFrames)}
+    with open(PARAMS['feature_opDir'] + '/' + name + '.pkl', 'wb') as f:
+        pickle.dump(stats, f, pickle.HIGHEST_PROTOCOL)
+    return stats
+
+
+def load_or_compute_data_stats(PARAMS, files, fold, loader=None, split='train'):
+    """Baseline_Results.py:607-621: reuse feature_opDir/data_stats_fold<k>_<n>class_train.pkl when present, else
+    run get_data_stats and write it.  Returns the dict the reference pickles."""
+    import pickle
+    name = 'data_stats_fold' + str(fold) + '_' + str(len(PARAMS['classes'])) + 'class_' + split
+    path = PARAMS['feature_opDir'] + '/' + name + '.pkl'
+    if os.path.exists(path):
+        with open(path, 'rb') as f:
+            return pickle.load(f)
+    mean, stdev, nMu, nSp, nSpMu = get_data_stats(PARAMS, files, loader=loader)
+    return save_data_stats(PARAMS, fold, mean, stdev, [nMu, nSp, nSpMu], split)

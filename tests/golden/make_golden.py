@@ -98,9 +98,21 @@ def main():
     PARAMS = {"Tw": 25, "Ts": 10, "Model": model, "l_harm": {model: 21}, "l_perc": {model: 11},
               "frame_level_scaling": False}
     # signal preparation (the step before the hot path)
+    _AUDIO["/d/speech/short.wav"] = make_wave(5, 0.06)            # below 0.1 s: exercises the doubling (:345-347)
+    _AUDIO["/d/music/onesil.wav"] = make_wave(6, 1.0, silent=[(0.4, 0.7)])   # ONE stretch: marked, not removed
+    out["audio:/d/speech/short.wav"] = _AUDIO["/d/speech/short.wav"]
+    out["audio:/d/music/onesil.wav"] = _AUDIO["/d/music/onesil.wav"]
+    tools = sys.modules["lib.cython_impl.tools"]
     for k in _AUDIO:
         x, fs = preproc.load_and_preprocess_signal(k, 25, 10)
         out["prep:" + k] = np.asarray(x, dtype=np.float32)
+        # the gate's intermediates straight from the reference's Cython leaf (tools.pyx:42-134)
+        y = preproc.normalize_signal(_AUDIO[k].copy())
+        energy = _rms(y=y, frame_length=400, hop_length=160)[0]
+        _, smark, fmark, _ = tools.removeSilence(y, len(y), energy, len(energy), 16000, 25, 10)
+        out["gate:frame:" + k] = np.asarray(fmark, dtype=np.int32)
+        out["gate:sample:" + k] = np.asarray(smark, dtype=np.uint8)
+        out["gate:energy:" + k] = np.asarray(energy, dtype=np.float32)
     mix = preproc.mix_signals(out["prep:/d/speech/sp0.wav"], out["prep:/d/music/mu0.wav"], 5)
     out["mix:sp0+mu0@5"] = np.asarray(mix, dtype=np.float32)
 
@@ -117,6 +129,14 @@ def main():
     fvm = preproc.get_featuregram(PARAMS, "music", "/nonexistent", "", "/d/music/mu1.wav", -1, 400, 40,
                                   "LogMelHarmPercSpec", save_feat=False)
     out["fv:music:LogMelHarmPercSpec"] = fvm
+    # the headline configuration of BASELINE.json configs[1]: 120 mel bands, median kernels 31 / 31
+    P31 = dict(PARAMS, l_harm={model: 31}, l_perc={model: 31})
+    out["fv120:speech:LogMelHarmPercSpec"] = preproc.get_featuregram(
+        P31, "speech", "/nonexistent", "/d/speech/sp1.wav", "", -1, 400, 120, "LogMelHarmPercSpec", save_feat=False)
+    out["fv120:speech_music:LogMelHarmPercSpec"] = preproc.get_featuregram(
+        P31, "speech_music", "/nonexistent", "/d/speech/sp1.wav", "/d/music/mu1.wav", -5, 400, 120,
+        "LogMelHarmPercSpec", save_feat=False)
+    # per-patch statistics of the skewness ablation (tools.pyx:169-211), from the reference's Cython leaf
 
     # NOTE: the reference standardises IN PLACE (StandardScaler(copy=False) on views of FV), i.e.
     # get_feature_patches mutates its argument; copies keep the golden featuregrams pristine.
@@ -153,8 +173,11 @@ def main():
             for f in sorted(os.listdir(os.path.join(td, cls))):
                 out[f"statsfv:{cls}:{f[:-4]}"] = np.load(os.path.join(td, cls, f))
     out["scaled:py"] = preproc.scale_data(FV, mean, std)
-    tools = sys.modules["lib.cython_impl.tools"]
     out["scaled:cy"] = tools.scale_data(FV, mean, std)
+    pat = out["patch:Lemaire_et_al_MTL:LogMelHarmPercSpec:49:24"]
+    for st in ("mean", "variance", "skew", "kurtosis"):
+        for ax in (0, 1):
+            out[f"pstat:{st}:{ax}"] = tools.get_data_statistics(pat, stat_type=st, axis=ax)
 
     path = os.path.join(HERE, "reference_glue.npz")
     np.savez_compressed(path, **out)

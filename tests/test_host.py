@@ -129,21 +129,46 @@ def test_feature_name_dispatch():
         feature_family("MFCC")                                                     # not in the reference
 
 
-def test_signal_preparation_matches_reference(tmp_path):
-    """normalise -> RMS -> silence removal (Cython semantics, incl. the tail of ones) -> normalise, and
-    SMR mixing, against the signals the reference's own functions produced."""
-    from sm_hpss_mtl_b200 import preprocessing as pp
+def test_oracle_signal_preparation_matches_reference():
+    """The oracle's restatement of normalise -> RMS -> silence removal (Cython semantics, incl. the tail of ones,
+    "more than one stretch", the doubling below 0.1 s) -> normalise, and of SMR mixing, against what the reference's
+    own functions (lib/preprocessing.py + its compiled Cython leaf) produced: signals AND the gate's markers."""
     g = np.load(GOLDEN)
     audio = {k[len("audio:"):]: g[k] for k in g.files if k.startswith("audio:")}
+    assert len(audio) == 6
     for path, x in audio.items():
-        got, fs = pp.load_and_preprocess_signal(path, 25, 10, loader=lambda p: audio[p].copy())
-        want = g["prep:" + path]
-        assert fs == 16000 and got.shape == want.shape
-        assert np.allclose(got, want, rtol=0, atol=1e-7), path
-    sp0 = g["prep:/d/speech/sp0.wav"]
-    assert not np.array_equal(sp0, pp.normalize_signal(audio["/d/speech/sp0.wav"]))   # silence really was removed
-    mix = pp.mix_signals(sp0, g["prep:/d/music/mu0.wav"], 5)
-    assert np.allclose(mix, g["mix:sp0+mu0@5"], rtol=0, atol=1e-6)
+        got, smark, fmark, energy = po.load_and_preprocess_signal(x, 25, 10, details=True)
+        assert got.shape == g["prep:" + path].shape
+        assert np.array_equal(got.astype(np.float32), g["prep:" + path]), path
+        assert np.array_equal(smark, g["gate:sample:" + path]) and np.array_equal(fmark, g["gate:frame:" + path])
+    assert g["prep:/d/speech/short.wav"].size == 2 * 960                     # doubled once: 0.06 s -> 0.12 s
+    assert (g["gate:sample:/d/music/onesil.wav"] == 0).any()                 # one stretch: marked ...
+    y = po.normalize_signal(audio["/d/music/onesil.wav"])
+    assert np.allclose(g["prep:/d/music/onesil.wav"], po.normalize_signal(y), atol=1e-7)   # ... but not removed
+    mix = po.mix_signals(g["prep:/d/speech/sp0.wav"], g["prep:/d/music/mu0.wav"], 5)
+    assert np.allclose(mix, g["mix:sp0+mu0@5"], rtol=0, atol=1e-7)
+    pat = g["patch:Lemaire_et_al_MTL:LogMelHarmPercSpec:49:24"]
+    for st in ("mean", "variance", "skew", "kurtosis"):
+        for ax in (0, 1):
+            assert np.array_equal(po.get_data_statistics(pat, st, ax), g[f"pstat:{st}:{ax}"])
+
+
+def test_prep_lengths_host_side(lib):
+    """hpss_prep_out_length / hpss_prep_num_frames (host-only entries) against the reference's rules."""
+    from sm_hpss_mtl_b200 import engine
+    for n in (2, 100, 799, 800, 960, 1599, 1600, 1601, 16000, 57_600_000):
+        want = n
+        while want / 16000 < 0.1:                                            # lib/preprocessing.py:345-347
+            want *= 2
+        assert engine.prep_out_length(n, 16000) == want
+        assert engine.prep_num_frames(n, 400, 160) == len(po.frame_rms(np.zeros(n, np.float32), 400, 160)) if n < 1_000_000 \
+            else engine.prep_num_frames(n, 400, 160) == 1 + n // 160
+    for T, W, sh in [(98, 249, 24), (249, 249, 24), (248, 249, 24), (5, 68, 68), (300, 68, 68), (67, 68, 68), (68, 68, 1)]:
+        Tt = T
+        if T < W:
+            while Tt <= W:                                                   # lib/preprocessing.py:139-142
+                Tt += T
+        assert engine.num_patches_tiled(T, W, sh) == len(range(W // 2, Tt - W // 2, sh))
 
 
 def test_load_audio_wav_roundtrip(tmp_path):
@@ -154,6 +179,24 @@ def test_load_audio_wav_roundtrip(tmp_path):
     wavfile.write(p, 16000, x)
     y = pp.load_audio(p)
     assert y.dtype == np.float32 and np.array_equal(y, x.astype(np.float32) / 32768.0)
+    z = pp.load_pcm(p)
+    assert z.dtype == np.int16 and np.array_equal(z, x)                      # 16-bit PCM stays int16 for the upload
+    wavfile.write(p, 8000, x)
+    assert pp.load_pcm(p).dtype == np.float32 and abs(len(pp.load_pcm(p)) - 8000) <= 1      # resampled to 16 kHz
+
+
+def test_stat_jobs_and_cache_names():
+    """File lists of get_data_stats and the cache-file stems, incl. the 5-class script's noise variants."""
+    from sm_hpss_mtl_b200 import preprocessing as pp
+    P = {"classes": {0: "music", 1: "speech", 2: "speech_music"}, "folder": "/d"}
+    files = {"music": ["m0.wav"], "speech": ["s0.wav"], "speech+music": [{"speech": "s0.wav", "music": "m0.wav", "SMR": 5}]}
+    jobs = pp._stat_jobs(P, files)
+    assert jobs == [("music", "", "/d/music/m0.wav", -1), ("speech", "/d/speech/s0.wav", "", -1),
+                    ("speech_music", "/d/speech/s0.wav", "/d/music/m0.wav", 5)]
+    assert pp._feature_name_of_file("/d/speech/s0.wav", "/d/music/m0.wav", 5) == "s0_m0_5dB"
+    assert pp._feature_name_of_file("/d/speech/s0.wav", "", 10, "/d/noise/n1.wav") == "s0_n1_10dB"
+    assert pp._feature_name_of_file("", "", -1, "/d/noise/n1.wav") == "n1"
+    assert pp._sources("speech_noise", "a", "b", "c") == ("a", "c") and pp._sources("noise", "a", "b", "c") == ("c", None)
 
 
 # ------------------------------------------------------------------ sharding + the one collective

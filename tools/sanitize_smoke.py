@@ -28,8 +28,6 @@ for (n_fft, win, hop, kh, kp) in [(400, 400, 160, 31, 31), (400, 400, 160, 21, 1
     harm = engine.median_time(batch, S, F, kh)
     perc = engine.median_freq(batch, S, F, kp)
     o1, cm = engine.mask_mel_log(batch, S, harm, perc, F, mel_sr=22050, n_mels=40, log_power=True)
-    if kp % 2 == 1 and kp <= 63:
-        o2, cm2 = engine.perc_mask_mel_log(batch, S, harm, F, kp, 22050, 40, log_power=1)
     engine.row_standardize(batch, out.clone(), D)
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
