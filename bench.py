@@ -384,7 +384,7 @@ def run_gpu(args):
     # ---- e2e_stats: decoded 16-bit PCM in host memory -> upload -> preparation (N2) -> features -> moments
     pcm_host = engine.host_alloc(n_clips * L, np.int16)
     pcm_host[:] = np.clip(np.round(wave_host * 30000.0), -32768, 32767).astype(np.int16)
-    spl = engine.Pipeline(ctx, [L] * n_clips, prm, pcm_dtype=np.int16, prepare=True, fs=CFG["fs"])
+    spl = engine.Pipeline(ctx, [L] * n_clips, prm, pcm_dtype=np.int16, prepare=True, fs=CFG["fs"], n_chunks=4)   # no feature download: few, large chunks (tools/dev/pipe_chunks.py)
     mom = np.zeros(3 * D + D + 3 + 1)
     for _ in range(2):
         spl.run(pcm_host, clip_class=classes, n_classes=3, moments=mom, want_features=False)

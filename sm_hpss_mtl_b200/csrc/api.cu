@@ -783,6 +783,7 @@ int hpss_pipeline_destroy(hpss_pipeline* pl) {
     cudaSetDevice(pl->ctx->device);
     cudaDeviceSynchronize();
     for (auto* sb : pl->subs) if (sb) hpss_batch_destroy(sb);
+    for (auto* pp : pl->prep_plans) prep_plan_free(pp);
     for (int i = 0; i < 2; ++i) if (pl->slot[i]) cudaFree(pl->slot[i]);
     if (pl->d_acc) cudaFree(pl->d_acc);
     if (pl->h_acc) cudaFreeHost(pl->h_acc);
@@ -840,6 +841,12 @@ int hpss_pipeline_create(hpss_ctx* ctx, const int64_t* clip_len, int32_t n_clips
         const int c0 = pl->cut[i], c1 = pl->cut[i + 1];
         rc = hpss_batch_from_samples(ctx, pl->wav_len.data() + c0, c1 - c0, p->n_fft, p->hop_length, &pl->subs[i]);
         if (rc) { hpss_pipeline_destroy(pl); return rc; }
+        if (prepare) {
+            PrepPlan* pp = nullptr;
+            rc = prep_plan_build(ctx, clip_len + c0, c1 - c0, fs, p->win_length, p->hop_length, &pp);
+            if (rc) { hpss_pipeline_destroy(pl); return rc; }
+            pl->prep_plans.push_back(pp);
+        }
         int64_t wav = 0;
         for (int c = c0; c < c1; ++c) wav += pl->wav_len[c];
         const int64_t frames = pl->frame_off[c1] - pl->frame_off[c0];
@@ -924,8 +931,8 @@ int hpss_pipeline_run(hpss_pipeline* pl, const void* pcm_host, float* feat_host,
         if (e == cudaSuccess && i >= 2 && feat_host) e = cudaStreamWaitEvent(ctx->s_comp, ctx->ev_d2h[s], 0);   // out slot free
         if (e != cudaSuccess) { cudaDeviceSynchronize(); return cuda_fail(e, "host pipeline (upload)"); }
         if (pl->prepare) {
-            rc = launch_prep(ctx, d_in, pl->pcm_format, pl->in_len.data() + c0, c1 - c0, pl->fs, p->win_length,
-                             p->hop_length, pl->alpha, pl->beta, d_wave, nullptr, nullptr, nullptr, ctx->s_comp);
+            rc = launch_prep_plan(ctx, pl->prep_plans[i], d_in, pl->pcm_format, pl->fs, p->win_length, p->hop_length,
+                                  pl->alpha, pl->beta, d_wave, ctx->s_comp);
         } else {
             int64_t wav = 0;
             for (int c = c0; c < c1; ++c) wav += pl->wav_len[c];

@@ -129,6 +129,8 @@ struct hpss_batch {
     std::map<std::pair<int, int>, std::pair<int2*, int64_t>> time_tiles;
 };
 
+namespace hpss { struct PrepPlan; }
+
 // Host-buffer pipeline (api.cu): clip chunks, their sub-batches and the double-buffered device slots
 struct hpss_pipeline {
     hpss_ctx* ctx = nullptr;
@@ -143,6 +145,7 @@ struct hpss_pipeline {
     std::vector<int64_t> frame_off;            // prefix of STFT frames
     std::vector<int> cut;                      // chunk i = clips [cut[i], cut[i+1])
     std::vector<hpss_batch*> subs;
+    std::vector<hpss::PrepPlan*> prep_plans;   // per chunk, when prepare
     size_t in_bytes = 0, wav_bytes = 0, out_bytes = 0;    // per-slot capacities (largest chunk)
     void* slot[2] = {nullptr, nullptr};
     double* d_acc = nullptr;                   // device moment accumulator
@@ -187,6 +190,15 @@ int64_t prep_num_frames(int64_t n, int win, int hop);
 int launch_prep(hpss_ctx* ctx, const void* pcm, int pcm_format, const int64_t* clip_len, int n_clips, int fs, int win,
                 int hop, double alpha, double beta, float* out, int32_t* frame_marker, uint8_t* sample_marker,
                 int32_t* n_sil, cudaStream_t st);
+struct PrepPlan {                  // prebuilt device descriptors of one batch of files (prep.cu)
+    int n_clips = 0;
+    size_t n_chunks = 0, n_tiles = 0, n_fr = 0, work_bytes = 0;
+    void* d_desc = nullptr;
+};
+int prep_plan_build(hpss_ctx* ctx, const int64_t* clip_len, int n_clips, int fs, int win, int hop, PrepPlan** out);
+void prep_plan_free(PrepPlan* pp);
+int launch_prep_plan(hpss_ctx* ctx, const PrepPlan* pp, const void* pcm, int pcm_format, int fs, int win, int hop,
+                     double alpha, double beta, float* out, cudaStream_t st);
 // mode 0: non-finite -> status bit 0; mode 1: negative -> status bit 1 (read by hpss_ctx_check)
 int launch_check(hpss_ctx* ctx, const float* x, int64_t n, int mode, cudaStream_t st);
 int launch_mix(hpss_ctx* ctx, const float* sp, const int64_t* sp_len, const float* mu, const int64_t* mu_len,

@@ -30,6 +30,7 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 8192;            // samples per CTA of the sample-level passes
 constexpr int kPerThread = kChunk / kThreads;
+constexpr int kBatch = 8;              // samples per thread in flight
 
 struct PrepClip {        // host-built, one per clip
     int64_t in_off;      // first sample in the input buffer
@@ -44,6 +45,8 @@ struct PrepClip {        // host-built, one per clip
     int64_t fm_off;      // first entry of this clip in the caller's (compact) frame-marker array
 };
 
+struct RmsTile { int32_t clip, t0, nt, pad_; };     // frames [t0, t0 + nt) of one clip
+
 struct PrepState {       // device-written, one per clip
     float mean1, peak1;
     uint32_t max_e;      // bits of the largest frame energy (non-negative floats order like their bits)
@@ -53,6 +56,7 @@ struct PrepState {       // device-written, one per clip
     int32_t removed;     // samples in the stored intervals
     int32_t n_kept;      // apply ? len - removed : len
     float mean2, peak2;
+    float rcp1, rcp2;    // refined reciprocals of peak1 / peak2 (0 when the peak is outside [2^-60, 2^60]: exact path)
 };
 
 struct Partial { double sum; float mn, mx; int32_t bad; int32_t pad_; };
@@ -76,6 +80,29 @@ template <> __device__ __forceinline__ float load_sample<int16_t>(const int16_t*
 
 __device__ __forceinline__ float norm1(float x, float mean, float peak) {
     return __fdiv_rn(__fsub_rn(x, mean), peak);           // (Xin - mean) / max|.| in float32 (:130-131)
+}
+
+// refined reciprocal of a divisor that is used for a whole clip (the first half of the in-range sequence of an
+// IEEE float32 division, maskmath.cuh::div_in_range); 0 when the divisor is outside [2^-60, 2^60]
+__device__ __forceinline__ float refined_rcp(float p) {
+    if (!(p >= 0x1p-60f && p <= 0x1p60f)) return 0.f;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+    const float e = __fmaf_rn(-p, r, 1.0f);
+    return __fmaf_rn(r, e, r);
+}
+// (x - mean) / peak, correctly rounded like norm1: quotient, exact remainder, correction on the FMA pipe while
+// the numerator is in range; the rare tiny / huge numerator (and a clip whose peak is out of range) divides exactly
+__device__ __noinline__ float div_exact(float a, float p) { return __fdiv_rn(a, p); }   // cold: one copy in the code
+__device__ __forceinline__ float norm_fast(float x, float mean, float peak, float r) {
+    const float a = __fsub_rn(x, mean);
+    // numerator (and divisor, see refined_rcp) in [2^-60, 2^60]: quotient, remainder and correction all stay in the
+    // normal range.  One unsigned compare on the exponent field; zero takes the exact path too (it is rare and cheap).
+    const uint32_t e = (__float_as_uint(a) >> 23) & 0xffu;
+    if (r == 0.f || e - 67u > 120u) return div_exact(a, peak);
+    const float q0 = __fmul_rn(a, r);
+    const float rem = __fmaf_rn(-peak, q0, a);
+    return __fmaf_rn(r, rem, q0);
 }
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -109,11 +136,16 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 struct Gate {
     const int32_t* k; const int32_t* l; const int32_t* rb;
     int n_iv, removed;
+    int ck, cl, crb;          // interval r, cached: [ck, cl) and the samples removed before it (r == n_iv: none)
+    __device__ __forceinline__ void fetch(int r) {
+        if (r < n_iv) { ck = __ldg(k + r); cl = __ldg(l + r); crb = __ldg(rb + r); }
+        else { ck = 0x7fffffff; cl = 0x7fffffff; crb = removed; }
+    }
 };
-__device__ __forceinline__ bool gate_locate(const Gate& g, int s, int& r, int& pos) {
-    while (r < g.n_iv && s >= __ldg(g.l + r)) ++r;
-    if (r < g.n_iv && s >= __ldg(g.k + r)) return false;
-    pos = s - (r < g.n_iv ? __ldg(g.rb + r) : g.removed);
+__device__ __forceinline__ bool gate_locate(Gate& g, int s, int& r, int& pos) {
+    while (s >= g.cl) g.fetch(++r);
+    if (s >= g.ck) return false;
+    pos = s - g.crb;
     return true;
 }
 
@@ -131,41 +163,47 @@ prep_reduce_kernel(const T* __restrict__ x, const PrepClip* __restrict__ clips, 
     const PrepClip cl = clips[ch.x];
     const int s0 = ch.y, s1 = min(cl.len, ch.y + kChunk);
     const T* xp = x + cl.in_off;
-    float mean1 = 0.f, peak1 = 1.f;
-    Gate g{nullptr, nullptr, nullptr, 0, 0};
+    float mean1 = 0.f, peak1 = 1.f, rcp1 = 1.f;
+    Gate g{nullptr, nullptr, nullptr, 0, 0, 0x7fffffff, 0x7fffffff, 0};
     int r = 0;
     if (MODE == 1) {
         const PrepState st = state[ch.x];
-        mean1 = st.mean1; peak1 = st.peak1;
+        mean1 = st.mean1; peak1 = st.peak1; rcp1 = st.rcp1;
         if (st.apply) {
-            g = Gate{fa.iv_k + cl.fr_off, fa.iv_l + cl.fr_off, fa.iv_rb + cl.fr_off, st.n_iv, st.removed};
+            g = Gate{fa.iv_k + cl.fr_off, fa.iv_l + cl.fr_off, fa.iv_rb + cl.fr_off, st.n_iv, st.removed, 0, 0, 0};
             r = __ldg(fa.blk_first + cl.fr_off + s0 / hop);
+            g.fetch(r);
         }
     }
     double sum = 0.0;
     float mn = INFINITY, mx = -INFINITY;
     int bad = 0;
-    float v[kPerThread];
+    // batches of kBatch samples per thread: the loads of a batch are issued together, the arithmetic of a batch is
+    // one basic block; the batch loop itself stays rolled (the unrolled kernel was four times the code and slower)
+#pragma unroll 1
+    for (int b0 = 0; b0 < kPerThread; b0 += kBatch) {
+        float v[kBatch];
 #pragma unroll
-    for (int i = 0; i < kPerThread; ++i) {
-        const int s = s0 + threadIdx.x + i * kThreads;
-        v[i] = s < s1 ? load_sample<T>(xp, s) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < kPerThread; ++i) {
-        const int s = s0 + threadIdx.x + i * kThreads;
-        if (s >= s1) continue;
-        float y = v[i];
-        if (MODE == 0) {
-            if (!isfinite(y)) { ++bad; continue; }
-        } else {
-            y = norm1(y, mean1, peak1);
-            int pos;
-            if (g.n_iv && !gate_locate(g, s, r, pos)) continue;
+        for (int i = 0; i < kBatch; ++i) {
+            const int s = s0 + threadIdx.x + (b0 + i) * kThreads;
+            v[i] = s < s1 ? load_sample<T>(xp, s) : 0.f;
         }
-        sum += (double)y;
-        mn = fminf(mn, y);
-        mx = fmaxf(mx, y);
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+            const int s = s0 + threadIdx.x + (b0 + i) * kThreads;
+            if (s >= s1) continue;
+            float y = v[i];
+            if (MODE == 0) {
+                if (!isfinite(y)) { ++bad; continue; }
+            } else {
+                y = norm_fast(y, mean1, peak1, rcp1);
+                int pos;
+                if (g.n_iv && !gate_locate(g, s, r, pos)) continue;
+            }
+            sum += (double)y;
+            mn = fminf(mn, y);
+            mx = fmaxf(mx, y);
+        }
     }
     sum = warp_sum_d(sum);
     mn = warp_min_f(mn);
@@ -208,6 +246,8 @@ prep_finalize_kernel(const PrepClip* __restrict__ clips, int n_clips, const Part
         if (bad) atomicOr(flags, 1u);                                     // HPSS_ERR_NONFINITE at the next hpss_ctx_check
         st.mean1 = (float)(sum / (double)cl.len);
         st.peak1 = fmaxf(fabsf(__fsub_rn(mx, st.mean1)), fabsf(__fsub_rn(mn, st.mean1)));
+        st.rcp1 = refined_rcp(st.peak1);
+        st.rcp2 = 0.f;
         st.max_e = 0u;
         st.n_sil = 0; st.n_iv = 0; st.apply = 0; st.removed = 0; st.n_kept = cl.len;
         st.mean2 = 0.f; st.peak2 = 1.f;
@@ -219,39 +259,54 @@ prep_finalize_kernel(const PrepClip* __restrict__ clips, int n_clips, const Part
         }
         st.mean2 = (float)(sum / (double)cl.len);
         st.peak2 = fmaxf(fabsf(__fsub_rn(mx, st.mean2)), fabsf(__fsub_rn(mn, st.mean2)));
+        st.rcp2 = refined_rcp(st.peak2);
     }
     state[c] = st;
 }
 
-// ---- P2: librosa.feature.rms(center=True): one warp per frame ----------------------------------------------
+// ---- P2: librosa.feature.rms(center=True): one CTA per tile of consecutive frames of one clip.  The squares of the
+// normalised samples of the tile's span ((nt - 1) * hop + win samples of the reflect-padded signal) are staged once in
+// shared memory -- every sample is loaded, normalised and squared once, not once per overlapping frame -- and each
+// warp then sums whole frames from there.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-prep_rms_kernel(const T* __restrict__ x, const PrepClip* __restrict__ clips, const int64_t* __restrict__ fr_off,
-                int n_clips, int64_t total_frames, PrepState* __restrict__ state, int win, int hop,
-                float* __restrict__ energy) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t gf = (int64_t)blockIdx.x * kWarps + warp;
-    if (gf >= total_frames) return;
-    const int c = find_clip(fr_off, n_clips, gf);
-    const PrepClip cl = clips[c];
-    const PrepState st = state[c];
-    const int t = (int)(gf - cl.fr_off);
-    if (t >= cl.n_frames) return;                          // padding entries of the per-frame arrays
+prep_rms_kernel(const T* __restrict__ x, const PrepClip* __restrict__ clips, const RmsTile* __restrict__ tiles,
+                PrepState* __restrict__ state, int win, int hop, float* __restrict__ energy) {
+    extern __shared__ float s_sq[];
+    __shared__ float s_max[kWarps];
+    const RmsTile tl = tiles[blockIdx.x];
+    const PrepClip cl = clips[tl.clip];
+    const PrepState st = state[tl.clip];
     const T* xp = x + cl.in_off;
-    const int first = t * hop - win / 2;                   // np.pad(y, frame_length // 2, mode='reflect')
-    const bool interior = first >= 0 && first + win <= cl.len;
-    float acc = 0.f;
-    for (int j = lane; j < win; j += 32) {
+    const int span = (tl.nt - 1) * hop + win;
+    const int first = tl.t0 * hop - win / 2;               // np.pad(y, frame_length // 2, mode='reflect')
+    const bool interior = first >= 0 && first + span <= cl.len;
+    // (batches of eight loads per thread were measured slower than this plain loop: 227 vs 184 us under ncu)
+#pragma unroll 4
+    for (int j = threadIdx.x; j < span; j += kThreads) {
         const int i = interior ? first + j : reflect101(first + j, cl.len);
-        const float y = norm1(load_sample<T>(xp, i), st.mean1, st.peak1);
-        acc = __fadd_rn(acc, __fmul_rn(y, y));             // np.abs(x)**2 rounds the square, then the sum
+        const float y = norm_fast(load_sample<T>(xp, i), st.mean1, st.peak1, st.rcp1);
+        s_sq[j] = __fmul_rn(y, y);                         // np.abs(x)**2 rounds the square, then the sum
     }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float emax = 0.f;
+    for (int t = warp; t < tl.nt; t += kWarps) {
+        const float* p = s_sq + t * hop;
+        float acc = 0.f;
+        for (int j = lane; j < win; j += 32) acc = __fadd_rn(acc, p[j]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         const float e = __fsqrt_rn(__fdiv_rn(acc, (float)win));
-        energy[gf] = e;
-        atomicMax(&state[c].max_e, __float_as_uint(e));    // e >= 0 (or NaN, which then poisons the threshold)
+        if (lane == 0) energy[cl.fr_off + tl.t0 + t] = e;
+        emax = e > emax || e != e ? e : emax;              // a NaN energy poisons the maximum (and the threshold)
+    }
+    if (lane == 0) s_max[warp] = emax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = 0.f;
+        for (int w = 0; w < kWarps; ++w) m = (s_max[w] > m || s_max[w] != s_max[w]) ? s_max[w] : m;
+        atomicMax(&state[tl.clip].max_e, __float_as_uint(m));    // e >= 0: non-negative floats order like their bits
     }
 }
 
@@ -383,29 +438,43 @@ prep_write_kernel(const T* __restrict__ x, const PrepClip* __restrict__ clips, c
     const int s0 = ch.y, s1 = min(cl.len, ch.y + kChunk);
     const T* xp = x + cl.in_off;
     float* op = out + cl.out_off;
-    Gate g{fa.iv_k + cl.fr_off, fa.iv_l + cl.fr_off, fa.iv_rb + cl.fr_off, st.n_iv, st.removed};
+    Gate g{fa.iv_k + cl.fr_off, fa.iv_l + cl.fr_off, fa.iv_rb + cl.fr_off, st.n_iv, st.removed, 0, 0, 0};
     int r = st.n_iv ? __ldg(fa.blk_first + cl.fr_off + s0 / hop) : 0;
+    g.fetch(r);
     const float tail = norm1(1.0f, st.mean2, st.peak2);
-    float v[kPerThread];
+#pragma unroll 1
+    for (int b0 = 0; b0 < kPerThread; b0 += kBatch) {
+        float v[kBatch];
 #pragma unroll
-    for (int i = 0; i < kPerThread; ++i) {
-        const int s = s0 + threadIdx.x + i * kThreads;
-        v[i] = s < s1 ? load_sample<T>(xp, s) : 0.f;
-    }
+        for (int i = 0; i < kBatch; ++i) {
+            const int s = s0 + threadIdx.x + (b0 + i) * kThreads;
+            v[i] = s < s1 ? load_sample<T>(xp, s) : 0.f;
+        }
 #pragma unroll
-    for (int i = 0; i < kPerThread; ++i) {
-        const int s = s0 + threadIdx.x + i * kThreads;
-        if (s >= s1) continue;
-        const float z = norm1(norm1(v[i], st.mean1, st.peak1), st.mean2, st.peak2);
-        int pos = s;
-        bool kept = true;
-        if (st.n_iv) kept = gate_locate(g, s, r, pos);
-        if (sample_marker) sample_marker[cl.in_off + s] = kept ? 1 : 0;
-        if (!st.apply) { pos = s; }
-        if (kept || !st.apply)
-            for (int q = 0; q < cl.rep; ++q) op[(int64_t)q * cl.len + pos] = z;
-        if (st.apply && s >= st.n_kept)
-            for (int q = 0; q < cl.rep; ++q) op[(int64_t)q * cl.len + s] = tail;
+        for (int i = 0; i < kBatch; ++i) {
+            const int s = s0 + threadIdx.x + (b0 + i) * kThreads;
+            if (s >= s1) continue;
+            const float z = norm_fast(norm_fast(v[i], st.mean1, st.peak1, st.rcp1), st.mean2, st.peak2, st.rcp2);
+            int pos = s;
+            bool kept = true;
+            if (st.n_iv) kept = gate_locate(g, s, r, pos);
+            if (sample_marker) sample_marker[cl.in_off + s] = kept ? 1 : 0;
+            if (!st.apply) { pos = s; }
+            if (kept || !st.apply) {
+                op[pos] = z;
+                if (cl.rep > 1) {                       // clips shorter than 0.1 s: the doubling (rare)
+#pragma unroll 1
+                    for (int q = 1; q < cl.rep; ++q) op[(int64_t)q * cl.len + pos] = z;
+                }
+            }
+            if (st.apply && s >= st.n_kept) {
+                op[s] = tail;
+                if (cl.rep > 1) {
+#pragma unroll 1
+                    for (int q = 1; q < cl.rep; ++q) op[(int64_t)q * cl.len + s] = tail;
+                }
+            }
+        }
     }
 }
 
@@ -583,75 +652,102 @@ template <typename T> static T* carve(char*& p, size_t count) {
     return r;
 }
 
-int launch_prep(hpss_ctx* ctx, const void* pcm, int pcm_format, const int64_t* clip_len, int n_clips, int fs, int win,
-                int hop, double alpha, double beta, float* out, int32_t* frame_marker, uint8_t* sample_marker,
-                int32_t* n_sil, cudaStream_t st) {
-    if (n_clips == 0) return HPSS_OK;
-    std::vector<PrepClip> clips(n_clips);
+namespace {
+
+struct PrepHost {                  // host-side layout of one batch of files
+    std::vector<PrepClip> clips;
     std::vector<int2> chunks;
+    std::vector<RmsTile> tiles;
+    size_t n_fr = 0;
+    int rms_tt = 1;                // frames per RMS tile (upper bound)
+};
+
+// frames per RMS tile: at most 32, and a span of at most ~12 K floats of shared memory
+int rms_tile_frames(int win, int hop) {
+    int tt = win < 12000 ? (12000 - win) / hop + 1 : 1;
+    return std::max(1, std::min(32, tt));
+}
+
+int prep_layout(const int64_t* clip_len, int n_clips, int fs, int win, int hop, PrepHost& h) {
+    h.clips.resize(n_clips);
+    h.chunks.clear();
+    h.tiles.clear();
+    h.rms_tt = rms_tile_frames(win, hop);
     int64_t in_off = 0, out_off = 0, fr_off = 0, fm_off = 0;
-    std::vector<int64_t> fr_offs(n_clips + 1, 0);
     for (int c = 0; c < n_clips; ++c) {
         const int64_t L = clip_len[c];
         if (L < 2 || L > 0x7fffffffLL / 2) {
             set_error("prep_signals: clip %d has %lld samples (need 2 .. 2^30)", c, (long long)L);
             return HPSS_ERR_INVALID;
         }
-        PrepClip& cl = clips[c];
+        PrepClip& cl = h.clips[c];
         cl.in_off = in_off; cl.out_off = out_off; cl.fr_off = fr_off;
         cl.len = (int32_t)L;
         const int64_t ol = prep_out_length(L, fs);
         cl.rep = (int32_t)(ol / L);
         cl.n_frames = (int32_t)prep_num_frames(L, win, hop);
-        cl.chunk0 = (int32_t)chunks.size();
+        cl.chunk0 = (int32_t)h.chunks.size();
         cl.n_chunks = (int32_t)((L + kChunk - 1) / kChunk);
         cl.pad_ = 0;
         cl.fm_off = fm_off;
         fm_off += cl.n_frames;
-        for (int64_t s = 0; s < L; s += kChunk) chunks.push_back(make_int2(c, (int)s));
+        for (int64_t s = 0; s < L; s += kChunk) h.chunks.push_back(make_int2(c, (int)s));
+        {   // RMS tiles: an even split of the clip's frames into tiles of at most rms_tt frames
+            const int nt = (cl.n_frames + h.rms_tt - 1) / h.rms_tt;
+            const int tt = nt > 0 ? (cl.n_frames + nt - 1) / nt : 0;
+            for (int t0 = 0; t0 < cl.n_frames; t0 += tt) h.tiles.push_back(RmsTile{c, t0, std::min(tt, cl.n_frames - t0), 0});
+        }
         in_off += L; out_off += ol;
-        // the per-frame arrays also serve as per-hop-block table: ceil(L/hop) <= n_frames + 1
+        // the per-frame arrays also serve as per-hop-block table: a clip owns max(n_frames, ceil(L/hop)) + 1 entries,
+        // of which [fr_off, fr_off + n_frames) are real frames
         fr_off += std::max<int64_t>(cl.n_frames, (L + hop - 1) / hop) + 1;
-        fr_offs[c + 1] = fr_off;
     }
-    const size_t n_chunks = chunks.size(), n_fr = (size_t)fr_off;
-    size_t bytes = align256(sizeof(PrepClip) * n_clips) + align256(sizeof(int2) * n_chunks) +
-                   align256(sizeof(int64_t) * (n_clips + 1)) + align256(sizeof(PrepState) * n_clips) +
-                   align256(sizeof(Partial) * n_chunks) + align256(sizeof(float) * n_fr) + align256(n_fr) +
-                   6 * align256(sizeof(int32_t) * n_fr) + 4096;
-    int rc = ensure_prep_scratch(ctx, bytes);
-    if (rc) return rc;
-    char* p = (char*)ctx->prep_ws;
-    PrepClip* d_clips = carve<PrepClip>(p, n_clips);
-    int2* d_chunks = carve<int2>(p, n_chunks);
-    int64_t* d_fr_off = carve<int64_t>(p, n_clips + 1);
-    PrepState* d_state = carve<PrepState>(p, n_clips);
-    Partial* d_partial = carve<Partial>(p, n_chunks);
+    h.n_fr = (size_t)fr_off;
+    return HPSS_OK;
+}
+
+size_t desc_bytes(int n_clips, size_t n_chunks, size_t n_tiles) {
+    return align256(sizeof(PrepClip) * std::max(n_clips, 1)) + align256(sizeof(int2) * std::max<size_t>(n_chunks, 1)) +
+           align256(sizeof(RmsTile) * std::max<size_t>(n_tiles, 1));
+}
+size_t work_bytes(int n_clips, size_t n_chunks, size_t n_fr) {
+    return align256(sizeof(PrepState) * std::max(n_clips, 1)) + align256(sizeof(Partial) * std::max<size_t>(n_chunks, 1)) +
+           align256(sizeof(float) * std::max<size_t>(n_fr, 1)) + align256(std::max<size_t>(n_fr, 1)) +
+           6 * align256(sizeof(int32_t) * std::max<size_t>(n_fr, 1));
+}
+
+// the seven launches; `desc` holds clips | chunks | fr_off, `work` the per-call scratch
+int prep_run(hpss_ctx* ctx, char* desc, char* work, int n_clips, size_t n_chunks, size_t n_tiles, size_t n_fr,
+             const void* pcm, int pcm_format, int fs, int win, int hop, double alpha, double beta, float* out,
+             int32_t* frame_marker, uint8_t* sample_marker, int32_t* n_sil, cudaStream_t st) {
+    PrepClip* d_clips = carve<PrepClip>(desc, n_clips);
+    int2* d_chunks = carve<int2>(desc, n_chunks);
+    RmsTile* d_tiles = carve<RmsTile>(desc, n_tiles);
+    PrepState* d_state = carve<PrepState>(work, n_clips);
+    Partial* d_partial = carve<Partial>(work, n_chunks);
     FrameArrays fa;
-    fa.energy = carve<float>(p, n_fr);
-    fa.marker = carve<uint8_t>(p, n_fr);
-    fa.run_a = carve<int32_t>(p, n_fr);
-    fa.run_b = carve<int32_t>(p, n_fr);
-    fa.iv_k = carve<int32_t>(p, n_fr);
-    fa.iv_l = carve<int32_t>(p, n_fr);
-    fa.iv_rb = carve<int32_t>(p, n_fr);
-    fa.blk_first = carve<int32_t>(p, n_fr);
-    // the RMS kernel looks a global frame up in the table of *frame* offsets; clips own max(n_frames, blocks)+1
-    // entries, frames [fr_off, fr_off + n_frames) are real
-    HPSS_CUDA(cudaMemcpyAsync(d_clips, clips.data(), sizeof(PrepClip) * n_clips, cudaMemcpyHostToDevice, st));
-    HPSS_CUDA(cudaMemcpyAsync(d_chunks, chunks.data(), sizeof(int2) * n_chunks, cudaMemcpyHostToDevice, st));
-    HPSS_CUDA(cudaMemcpyAsync(d_fr_off, fr_offs.data(), sizeof(int64_t) * (n_clips + 1), cudaMemcpyHostToDevice, st));
-    // pageable sources: the copies above have consumed the host vectors when the calls return
+    fa.energy = carve<float>(work, n_fr);
+    fa.marker = carve<uint8_t>(work, n_fr);
+    fa.run_a = carve<int32_t>(work, n_fr);
+    fa.run_b = carve<int32_t>(work, n_fr);
+    fa.iv_k = carve<int32_t>(work, n_fr);
+    fa.iv_l = carve<int32_t>(work, n_fr);
+    fa.iv_rb = carve<int32_t>(work, n_fr);
+    fa.blk_first = carve<int32_t>(work, n_fr);
     const unsigned g_chunks = (unsigned)n_chunks, g_clips = (unsigned)((n_clips + kWarps - 1) / kWarps);
-    const unsigned g_frames = (unsigned)((n_fr + kWarps - 1) / kWarps);
+    const size_t rms_smem = sizeof(float) * ((size_t)(rms_tile_frames(win, hop) - 1) * hop + win);
     const bool s16 = pcm_format == HPSS_PCM_S16;
+    if (rms_smem > 48 * 1024) {
+        if (s16) HPSS_CUDA(cudaFuncSetAttribute(prep_rms_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rms_smem));
+        else HPSS_CUDA(cudaFuncSetAttribute(prep_rms_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rms_smem));
+    }
     if (s16) prep_reduce_kernel<int16_t, 0><<<g_chunks, kThreads, 0, st>>>((const int16_t*)pcm, d_clips, d_chunks, d_state, fa, hop, d_partial);
     else prep_reduce_kernel<float, 0><<<g_chunks, kThreads, 0, st>>>((const float*)pcm, d_clips, d_chunks, d_state, fa, hop, d_partial);
     HPSS_LAUNCHED("prep_reduce_kernel");
     prep_finalize_kernel<0><<<g_clips, kThreads, 0, st>>>(d_clips, n_clips, d_partial, d_state, ctx->d_flags);
     HPSS_LAUNCHED("prep_finalize_kernel");
-    if (s16) prep_rms_kernel<int16_t><<<g_frames, kThreads, 0, st>>>((const int16_t*)pcm, d_clips, d_fr_off, n_clips, (int64_t)n_fr, d_state, win, hop, fa.energy);
-    else prep_rms_kernel<float><<<g_frames, kThreads, 0, st>>>((const float*)pcm, d_clips, d_fr_off, n_clips, (int64_t)n_fr, d_state, win, hop, fa.energy);
+    if (s16) prep_rms_kernel<int16_t><<<(unsigned)n_tiles, kThreads, rms_smem, st>>>((const int16_t*)pcm, d_clips, d_tiles, d_state, win, hop, fa.energy);
+    else prep_rms_kernel<float><<<(unsigned)n_tiles, kThreads, rms_smem, st>>>((const float*)pcm, d_clips, d_tiles, d_state, win, hop, fa.energy);
     HPSS_LAUNCHED("prep_rms_kernel");
     prep_gate_kernel<<<(unsigned)n_clips, kGateThreads, 0, st>>>(d_clips, d_state, fa, fs, win, hop, alpha, beta, frame_marker, n_sil);
     HPSS_LAUNCHED("prep_gate_kernel");
@@ -664,6 +760,78 @@ int launch_prep(hpss_ctx* ctx, const void* pcm, int pcm_format, const int64_t* c
     else prep_write_kernel<float><<<g_chunks, kThreads, 0, st>>>((const float*)pcm, d_clips, d_chunks, d_state, fa, hop, out, sample_marker);
     HPSS_LAUNCHED("prep_write_kernel");
     return HPSS_OK;
+}
+
+int upload_desc(const PrepHost& h, char* desc, cudaStream_t st, bool sync) {
+    const int n_clips = (int)h.clips.size();
+    PrepClip* d_clips = carve<PrepClip>(desc, n_clips);
+    int2* d_chunks = carve<int2>(desc, h.chunks.size());
+    RmsTile* d_tiles = carve<RmsTile>(desc, h.tiles.size());
+    if (sync) {
+        HPSS_CUDA(cudaMemcpy(d_clips, h.clips.data(), sizeof(PrepClip) * n_clips, cudaMemcpyHostToDevice));
+        HPSS_CUDA(cudaMemcpy(d_chunks, h.chunks.data(), sizeof(int2) * h.chunks.size(), cudaMemcpyHostToDevice));
+        HPSS_CUDA(cudaMemcpy(d_tiles, h.tiles.data(), sizeof(RmsTile) * h.tiles.size(), cudaMemcpyHostToDevice));
+    } else {
+        // pageable sources: the copies have consumed the host vectors when the calls return
+        HPSS_CUDA(cudaMemcpyAsync(d_clips, h.clips.data(), sizeof(PrepClip) * n_clips, cudaMemcpyHostToDevice, st));
+        HPSS_CUDA(cudaMemcpyAsync(d_chunks, h.chunks.data(), sizeof(int2) * h.chunks.size(), cudaMemcpyHostToDevice, st));
+        HPSS_CUDA(cudaMemcpyAsync(d_tiles, h.tiles.data(), sizeof(RmsTile) * h.tiles.size(), cudaMemcpyHostToDevice, st));
+    }
+    return HPSS_OK;
+}
+
+}  // namespace
+
+// one-shot: descriptors and scratch both live in the context's preparation scratch
+int launch_prep(hpss_ctx* ctx, const void* pcm, int pcm_format, const int64_t* clip_len, int n_clips, int fs, int win,
+                int hop, double alpha, double beta, float* out, int32_t* frame_marker, uint8_t* sample_marker,
+                int32_t* n_sil, cudaStream_t st) {
+    if (n_clips == 0) return HPSS_OK;
+    PrepHost h;
+    int rc = prep_layout(clip_len, n_clips, fs, win, hop, h);
+    if (rc) return rc;
+    const size_t db = desc_bytes(n_clips, h.chunks.size(), h.tiles.size());
+    rc = ensure_prep_scratch(ctx, db + work_bytes(n_clips, h.chunks.size(), h.n_fr) + 4096);
+    if (rc) return rc;
+    char* desc = (char*)ctx->prep_ws;
+    rc = upload_desc(h, desc, st, false);
+    if (rc) return rc;
+    return prep_run(ctx, desc, desc + db, n_clips, h.chunks.size(), h.tiles.size(), h.n_fr, pcm, pcm_format, fs, win, hop,
+                    alpha, beta, out, frame_marker, sample_marker, n_sil, st);
+}
+
+// prebuilt descriptors for repeated use (the host pipeline): nothing is uploaded on the launch path
+int prep_plan_build(hpss_ctx* ctx, const int64_t* clip_len, int n_clips, int fs, int win, int hop, PrepPlan** out) {
+    *out = nullptr;
+    PrepHost h;
+    int rc = prep_layout(clip_len, n_clips, fs, win, hop, h);
+    if (rc) return rc;
+    PrepPlan* pp = new PrepPlan();
+    pp->n_clips = n_clips; pp->n_chunks = h.chunks.size(); pp->n_tiles = h.tiles.size(); pp->n_fr = h.n_fr;
+    pp->work_bytes = work_bytes(n_clips, h.chunks.size(), h.n_fr) + 4096;
+    cudaError_t e = cudaMalloc(&pp->d_desc, desc_bytes(n_clips, h.chunks.size(), h.tiles.size()));
+    if (e != cudaSuccess) { cudaGetLastError(); delete pp; set_error("out of device memory: preparation descriptors"); return HPSS_ERR_NOMEM; }
+    rc = upload_desc(h, (char*)pp->d_desc, nullptr, true);
+    if (rc) { cudaFree(pp->d_desc); delete pp; return rc; }
+    rc = ensure_prep_scratch(ctx, pp->work_bytes);
+    if (rc) { cudaFree(pp->d_desc); delete pp; return rc; }
+    *out = pp;
+    return HPSS_OK;
+}
+
+void prep_plan_free(PrepPlan* pp) {
+    if (!pp) return;
+    if (pp->d_desc) cudaFree(pp->d_desc);
+    delete pp;
+}
+
+int launch_prep_plan(hpss_ctx* ctx, const PrepPlan* pp, const void* pcm, int pcm_format, int fs, int win, int hop,
+                     double alpha, double beta, float* out, cudaStream_t st) {
+    if (pp->n_clips == 0) return HPSS_OK;
+    int rc = ensure_prep_scratch(ctx, pp->work_bytes);     // no-op unless another caller shrank nothing: grow-only
+    if (rc) return rc;
+    return prep_run(ctx, (char*)pp->d_desc, (char*)ctx->prep_ws, pp->n_clips, pp->n_chunks, pp->n_tiles, pp->n_fr, pcm,
+                    pcm_format, fs, win, hop, alpha, beta, out, nullptr, nullptr, nullptr, st);
 }
 
 int launch_mix(hpss_ctx* ctx, const float* sp, const int64_t* sp_len, const float* mu, const int64_t* mu_len,

@@ -311,11 +311,17 @@ def prep_signals(ctx: Context, pcm: torch.Tensor, clip_lengths: Sequence[int], f
         raise ValueError(f"pcm must be float32 or int16, got {pcm.dtype}")
     if int(lens.sum()) != pcm.numel():
         raise ValueError(f"pcm has {pcm.numel()} samples, clip_lengths sum to {int(lens.sum())}")
-    out_len = [prep_out_length(int(n), fs) for n in lens]
-    out = torch.empty(int(sum(out_len)), dtype=torch.float32, device=pcm.device)
+    ol = lens.copy()                                     # hpss_prep_out_length, vectorised (lib/preprocessing.py:345-347)
+    while True:
+        short = ol / float(fs) < 0.1
+        if not short.any():
+            break
+        ol[short] *= 2
+    out_len = [int(v) for v in ol]
+    out = torch.empty(int(ol.sum()), dtype=torch.float32, device=pcm.device)
     fm = sm = ns = None
     if markers:
-        nfr = sum(prep_num_frames(int(n), win_length, hop_length) for n in lens)
+        nfr = int((1 + (lens + 2 * (win_length // 2) - win_length) // hop_length).sum())      # hpss_prep_num_frames
         fm = torch.zeros(nfr, dtype=torch.int32, device=pcm.device)
         sm = torch.zeros(pcm.numel(), dtype=torch.uint8, device=pcm.device)
         ns = torch.zeros(max(1, lens.size), dtype=torch.int32, device=pcm.device)
