@@ -298,6 +298,74 @@ __device__ __forceinline__ void tile_fill_async(uint32_t sm_base, const float* _
     }
 }
 
+// selection networks of one tile: lane = line, the TT + K - 1 inputs of the line sit at sm[sidx(lane, pos)];
+// outputs overwrite the line in place (time axis) or go straight to global memory (frequency axis)
+template <int K, bool TIME_AXIS>
+__device__ __forceinline__ void median_compute_tile(float* __restrict__ sm, float* __restrict__ out, const LineInfo& li,
+                                                    int lane, int p0, int TT, int lstride) {
+    constexpr int G = MedianGroup<K>::G;
+    constexpr bool STEP = TIME_AXIS && MedianStep<K>::available;
+    constexpr int GS = MedianStep<K>::G;
+    constexpr bool MIXED = STEP && GS == G;
+    const int NG = TT / G;
+    const bool live = li.n > 0 && p0 < li.n;
+    if (live) {
+        const int ng = min(NG, (li.n - p0 + G - 1) / G);
+        int g = 0;
+        if constexpr (STEP) {
+            // stateful walk: two groups per step, the sorted blocks C2, C3 of one step are C0, C1 of the next
+            constexpr int NR = MedianStep<K>::NRAW;
+            const int live = min(TT, li.n - p0);                       // outputs this line needs
+            const int nst = MIXED ? ng / 2 : (live + 2 * GS - 1) / (2 * GS);
+            if (nst > 0) {
+                float ca[GS], cb[GS];
+                {
+                    float r0[GS], r1[GS];
+#pragma unroll
+                    for (int i = 0; i < GS; ++i) {
+                        r0[i] = sm[sidx<TIME_AXIS>(lane, GS - 1 + i, lstride)];
+                        r1[i] = sm[sidx<TIME_AXIS>(lane, 2 * GS - 1 + i, lstride)];
+                    }
+                    MedianStep<K>::sort(r0, ca);
+                    MedianStep<K>::sort(r1, cb);
+                }
+                for (int st = 0; st < nst; ++st) {
+                    const int b0 = 2 * GS * st;
+                    float xr[NR], o[2 * GS], na[GS], nb[GS];
+#pragma unroll
+                    for (int i = 0; i < NR; ++i)
+                        xr[i] = sm[sidx<TIME_AXIS>(lane, b0 + MedianStep<K>::raw_pos(i), lstride)];
+                    MedianStep<K>::run(ca, cb, xr, o, na, nb);
+#pragma unroll
+                    for (int i = 0; i < GS; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
+#pragma unroll
+                    for (int j = 0; j < 2 * GS; ++j) sm[sidx<TIME_AXIS>(lane, b0 + j, lstride)] = o[j];
+                }
+            }
+            g = MIXED ? 2 * nst : ng;                                 // !MIXED: the steps covered the tile
+        }
+        for (; g < ng; ++g) {
+            float x[K + G - 1], o[G];
+#pragma unroll
+            for (int i = 0; i < K + G - 1; ++i) x[i] = sm[sidx<TIME_AXIS>(lane, g * G + i, lstride)];
+            MedianGroup<K>::run(x, o);
+            if (TIME_AXIS) {
+                // in place: a lane's outputs are consecutive in time, the coalesced store needs the
+                // transposed view of the tile (tile_store below)
+#pragma unroll
+                for (int j = 0; j < G; ++j) sm[sidx<TIME_AXIS>(lane, g * G + j, lstride)] = o[j];
+            } else {
+                // lane = frame: registers -> global memory is already one 128-byte row segment per output
+                float* dst = out + li.base + (int64_t)(p0 + g * G) * li.estride;
+                const int nj = min(G, li.n - p0 - g * G);
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+                    if (j < nj) dst[(int64_t)j * li.estride] = o[j];
+            }
+        }
+    }
+}
+
 template <int K, bool TIME_AXIS>
 __global__ void __launch_bounds__(kRingThreads, 1)
 median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const int64_t* __restrict__ frame_off,
@@ -381,68 +449,144 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
                 li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane, uniform_T);
                 li_lb = lb;
             }
-            const bool live = li.n > 0 && p0 < li.n;
             mbar_wait(full0 + 8u * b, use & 1u);
-            if (live) {
-                const int ng = min(NG, (li.n - p0 + G - 1) / G);
-                int g = 0;
-                if constexpr (STEP) {
-                    // stateful walk: two groups per step, the sorted blocks C2, C3 of one step are C0, C1 of the next
-                    constexpr int NR = MedianStep<K>::NRAW;
-                    const int live = min(TT, li.n - p0);                       // outputs this line needs
-                    const int nst = MIXED ? ng / 2 : (live + 2 * GS - 1) / (2 * GS);
-                    if (nst > 0) {
-                        float ca[GS], cb[GS];
-                        {
-                            float r0[GS], r1[GS];
-#pragma unroll
-                            for (int i = 0; i < GS; ++i) {
-                                r0[i] = sm[sidx<TIME_AXIS>(lane, GS - 1 + i, lstride)];
-                                r1[i] = sm[sidx<TIME_AXIS>(lane, 2 * GS - 1 + i, lstride)];
-                            }
-                            MedianStep<K>::sort(r0, ca);
-                            MedianStep<K>::sort(r1, cb);
-                        }
-                        for (int st = 0; st < nst; ++st) {
-                            const int b0 = 2 * GS * st;
-                            float xr[NR], o[2 * GS], na[GS], nb[GS];
-#pragma unroll
-                            for (int i = 0; i < NR; ++i)
-                                xr[i] = sm[sidx<TIME_AXIS>(lane, b0 + MedianStep<K>::raw_pos(i), lstride)];
-                            MedianStep<K>::run(ca, cb, xr, o, na, nb);
-#pragma unroll
-                            for (int i = 0; i < GS; ++i) { ca[i] = na[i]; cb[i] = nb[i]; }
-#pragma unroll
-                            for (int j = 0; j < 2 * GS; ++j) sm[sidx<TIME_AXIS>(lane, b0 + j, lstride)] = o[j];
-                        }
-                    }
-                    g = MIXED ? 2 * nst : ng;                                 // !MIXED: the steps covered the tile
-                }
-                for (; g < ng; ++g) {
-                    float x[K + G - 1], o[G];
-#pragma unroll
-                    for (int i = 0; i < K + G - 1; ++i) x[i] = sm[sidx<TIME_AXIS>(lane, g * G + i, lstride)];
-                    MedianGroup<K>::run(x, o);
-                    if (TIME_AXIS) {
-                        // in place: a lane's outputs are consecutive in time, the coalesced store needs the
-                        // transposed view of the tile (tile_store below)
-#pragma unroll
-                        for (int j = 0; j < G; ++j) sm[sidx<TIME_AXIS>(lane, g * G + j, lstride)] = o[j];
-                    } else {
-                        // lane = frame: registers -> global memory is already one 128-byte row segment per output
-                        float* dst = out + li.base + (int64_t)(p0 + g * G) * li.estride;
-                        const int nj = min(G, li.n - p0 - g * G);
-#pragma unroll
-                        for (int j = 0; j < G; ++j)
-                            if (j < nj) dst[(int64_t)j * li.estride] = o[j];
-                    }
-                }
-            }
+            median_compute_tile<K, TIME_AXIS>(sm, out, li, lane, p0, TT, lstride);
             __syncwarp();
             if (TIME_AXIS) {
                 tile_store<TIME_AXIS>(sm, out, li, lane, p0, TT, lstride);
                 __syncwarp();
             }
+            if (lane == 0) mbar_arrive(empty0 + 8u * b);
+        }
+    }
+}
+
+// ---- dense path (time axis, batches of equal clips whose whole line fits one tile: the training-segment shape) -----
+// The 32 lines of a tile are 32 consecutive rows of T floats = ONE contiguous, 16-byte aligned chunk of 128 * T bytes,
+// so a single elected thread fetches the whole tile with one bulk asynchronous copy (cp.async.bulk, completion counted
+// in bytes on an mbarrier) into a small ring of dense landing buffers.  The loader warps then only re-lay the tile
+// inside shared memory -- dense rows -> rows with the reflected halo and an odd stride (LDS + STS, the reflected
+// source offsets of a lane's positions live in registers) -- instead of gathering it from global memory with
+// 4-byte cp.async (one copy per ~75 cycles and warp: the loader ring was the limit of this kernel for k <= 31).
+// Compute warps, selection networks and the coalesced store are those of median_fast_kernel.
+#ifndef HPSS_LAND
+#define HPSS_LAND 3
+#endif
+constexpr int kLand = HPSS_LAND;  // landing buffers
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+template <int K>
+__global__ void __launch_bounds__(kRingThreads, 1)
+median_dense_kernel(const float* __restrict__ S, float* __restrict__ out, int64_t n_lines, int T, int TT, int64_t n_items,
+                    int NB) {
+    constexpr int HALO = K / 2;
+    extern __shared__ __align__(128) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int span = TT + K - 1;
+    const int lstride = span | 1;
+    const int tile_floats = 32 * lstride;
+    const int land_floats = (32 * T + 31) & ~31;                  // 128-byte multiples keep every buffer 16-byte aligned
+    float* land0 = smem + (((size_t)NB * tile_floats + 31) & ~(size_t)31);     // the base is 128-byte aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(land0 + (size_t)kLand * land_floats);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NB);
+    const uint32_t lfull0 = smem_u32(bars + 2 * NB), lempty0 = smem_u32(bars + 2 * NB + kLand);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NB; ++b) {
+            mbar_init(full0 + 8u * b, 32 * kLoaderWarps);         // every loader lane arrives after its stores
+            mbar_init(empty0 + 8u * b, 1);                        // one consumer lane releases the buffer
+        }
+        for (int b = 0; b < kLand; ++b) {
+            mbar_init(lfull0 + 8u * b, 1);                        // the issuing thread's expect_tx arrival + the bytes
+            mbar_init(lempty0 + 8u * b, kLoaderWarps);            // every loader warp has read the landing buffer
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t my_items = (n_items > blockIdx.x) ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto tile_rows = [&](int64_t item) { return (int)min((int64_t)32, n_lines - item * 32); };
+
+    if (warp >= kComputeWarps) {
+        // ===== loader warps =====
+        const int lw = warp - kComputeWarps;
+        // reflected source BYTE offset (within a dense row) of this lane's positions; (p0, n) = (0, T) for every tile
+        uint32_t off4[FillCache::kChunks];
+#pragma unroll
+        for (int q = 0; q < FillCache::kChunks; ++q) off4[q] = 4u * (uint32_t)reflect_idx(lane + 32 * q - HALO, T);
+        auto issue = [&](int64_t n) {                              // elected thread: bulk copy of item n
+            const int slot = (int)(n % kLand);
+            const uint32_t use = (uint32_t)(n / kLand);
+            if (use > 0) mbar_wait(lempty0 + 8u * slot, (use - 1) & 1u);
+            const int64_t item = blockIdx.x + n * gridDim.x;
+            const uint32_t bytes = ((uint32_t)tile_rows(item) * (uint32_t)T * 4u) & ~15u;
+            mbar_expect_tx(lfull0 + 8u * slot, bytes);
+            if (bytes) bulk_load(smem_u32(land0 + (size_t)slot * land_floats), S + item * 32 * (int64_t)T, bytes, lfull0 + 8u * slot);
+        };
+        const bool elected = lw == 0 && lane == 0;
+        if (elected)
+            for (int64_t n = 0; n < min((int64_t)(kLand - 1), my_items); ++n) issue(n);
+        for (int64_t n = 0; n < my_items; ++n) {
+            if (elected && n + kLand - 1 < my_items) issue(n + kLand - 1);
+            const int slot = (int)(n % kLand);
+            const int b = (int)(n % NB);
+            const uint32_t use = (uint32_t)(n / NB);
+            const int64_t item = blockIdx.x + n * gridDim.x;
+            const int rows_here = tile_rows(item);
+            const float* land = land0 + (size_t)slot * land_floats;
+            mbar_wait(lfull0 + 8u * slot, (uint32_t)(n / kLand) & 1u);
+            {   // the (at most three) floats behind the last 16-byte unit of a partial last tile
+                const int got = (int)((((uint32_t)rows_here * (uint32_t)T * 4u) & ~15u) / 4u), want = rows_here * T;
+                if (lw == 0 && got + lane < want)
+                    const_cast<float*>(land)[got + lane] = __ldg(S + item * 32 * (int64_t)T + got + lane);
+                if (got != want) asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kLoaderWarps) : "memory");
+            }
+            if (use > 0) mbar_wait(empty0 + 8u * b, (use - 1) & 1u);
+            // 32-bit shared-memory addresses: one add per access (generic pointers cost four ALU instructions each)
+            uint32_t src = smem_u32(land) + 4u * (uint32_t)(lw * T);
+            uint32_t dst = smem_u32(smem + (size_t)b * tile_floats) + 4u * (uint32_t)(lw * lstride + lane);
+            const uint32_t sstep = 4u * (uint32_t)(kLoaderWarps * T), dstep = 4u * (uint32_t)(kLoaderWarps * lstride);
+            // (four rows per iteration, all loads before the first store, was measured slower: 0.32 vs 0.24 ms at k = 31)
+            for (int r = lw; r < rows_here; r += kLoaderWarps, src += sstep, dst += dstep) {
+                float v[FillCache::kChunks];
+#pragma unroll
+                for (int q = 0; q < FillCache::kChunks; ++q) v[q] = (lane + 32 * q < span) ? lds_f32(src + off4[q]) : 0.f;
+#pragma unroll
+                for (int q = 0; q < FillCache::kChunks; ++q) if (lane + 32 * q < span) sts_f32(dst + 128u * q, v[q]);
+            }
+            mbar_arrive(full0 + 8u * b);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(lempty0 + 8u * slot);
+        }
+    } else {
+        // ===== compute warps =====
+        for (int64_t n = warp; n < my_items; n += kComputeWarps) {
+            const int b = (int)(n % NB);
+            const uint32_t use = (uint32_t)(n / NB);
+            float* sm = smem + (size_t)b * tile_floats;
+            const int64_t item = blockIdx.x + n * gridDim.x;
+            LineInfo li;
+            li.estride = 1;
+            li.n = (item * 32 + lane < n_lines) ? T : 0;
+            li.base = (item * 32 + lane) * (int64_t)T;
+            mbar_wait(full0 + 8u * b, use & 1u);
+            median_compute_tile<K, true>(sm, out, li, lane, 0, TT, lstride);
+            __syncwarp();
+            tile_store<true>(sm, out, li, lane, 0, TT, lstride);
+            __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8u * b);
         }
     }
@@ -554,6 +698,28 @@ int launch_fast(hpss_ctx* ctx, const hpss_batch* b, const float* S, float* out, 
     }
     const int span = TT + K - 1;
     const size_t tile_bytes = (TIME_AXIS ? (size_t)32 * (span | 1) : (size_t)span * 32) * sizeof(float);
+    if constexpr (TIME_AXIS) {
+        // equal clips whose whole line fits one tile, 16-byte aligned input: one bulk copy per tile (median_dense_kernel)
+        // (measured on the 4096 x 1 s batch: k = 31 0.248 -> 0.242 ms, k = 41 0.351 -> 0.339 ms, but k = 21 0.224 -> 0.231 ms
+        // and k = 11 0.201 -> 0.212 ms: below ~25 taps the tile period is too short for the two-stage pipeline)
+        if (K >= 25 && uniform_T > 0 && n_ptiles == 1 && span <= 32 * FillCache::kChunks && !knobs().no_dense_median &&
+            (reinterpret_cast<uintptr_t>(S) & 15) == 0) {
+            const size_t land_bytes = (((size_t)32 * uniform_T + 31) & ~(size_t)31) * sizeof(float);
+            const size_t fixed = kLand * land_bytes + 128 + 16 * (size_t)kLand + 256;
+            int NBd = (int)(((size_t)ctx->max_smem_optin - fixed) / (tile_bytes + 16));
+            if (NBd > 2 * kComputeWarps) NBd = 2 * kComputeWarps;
+            if (NBd >= kComputeWarps + 1) {
+                const size_t smem_d = (size_t)NBd * tile_bytes + fixed + (size_t)NBd * 16;
+                auto kd = median_dense_kernel<K>;
+                HPSS_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+                int64_t gd = (n_lb + kComputeWarps - 1) / kComputeWarps;
+                if (gd > ctx->sm_count) gd = ctx->sm_count;
+                kd<<<(unsigned)gd, kRingThreads, smem_d, st>>>(S, out, n_lines, uniform_T, TT, n_lb, NBd);
+                HPSS_LAUNCHED("median_dense_kernel");
+                return HPSS_OK;
+            }
+        }
+    }
     int NB = (int)(((size_t)ctx->max_smem_optin - 512) / (tile_bytes + 16));
     if (NB > 2 * kComputeWarps) NB = 2 * kComputeWarps;
     const size_t smem = (size_t)NB * tile_bytes + (size_t)NB * 16;
