@@ -365,3 +365,26 @@ def test_workspace_is_safe_across_streams(ctx):
     torch.cuda.synchronize()
     for a, b in outs:
         assert torch.equal(a, r1) and torch.equal(b, r2)
+
+
+def test_long_stream_time_split_equals_whole(ctx):
+    """configs[3] across ranks: a stream cut along time with l_harm // 2 halo frames per side and a MAX all-reduce of
+    the two per-stream maxima gives, shard by shard, exactly the columns of the unsharded featuregram."""
+    from sm_hpss_mtl_b200 import dist as hd
+    n_fft, hop, k = 2048, 512, 31
+    L = 16000 * 40
+    wave = torch.from_numpy(synth.synth_clip(5, L)).cuda()
+    prm = engine.make_params(n_fft=n_fft, win_length=n_fft, hop_length=hop, l_harm=k, l_perc=k, n_mels=120)
+    batch = engine.Batch(ctx, clip_lengths=[L], n_fft=n_fft, hop_length=hop)
+    whole = engine.featuregram(batch, wave, prm).view(240, -1)
+    for world in (2, 3, 8):
+        shards = [hd.stream_shard(L, n_fft, hop, k, r, world) for r in range(world)]
+        assert shards[0][0][0] == 0 and shards[-1][0][1] == whole.shape[1]
+        # pass 1: every "rank" publishes its maxima; pass 2 applies the stream-wide maximum (what the all-reduce does)
+        maxima = []
+        for sh in shards:
+            hd.featuregram_stream_sharded(ctx, wave[sh[2][0]:sh[2][1]], sh, prm, allreduce_max=lambda m: maxima.append(m.clone()))
+        gmax = torch.stack(maxima).amax(dim=0)
+        for sh in shards:
+            got = hd.featuregram_stream_sharded(ctx, wave[sh[2][0]:sh[2][1]], sh, prm, allreduce_max=lambda m: m.copy_(gmax))
+            assert torch.equal(got, whole[:, sh[0][0]:sh[0][1]]), (world, sh[0])

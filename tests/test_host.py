@@ -214,6 +214,26 @@ def test_shard_clips_properties():
     assert shard_clips([16000] * 4096, 8) == [(i * 512, (i + 1) * 512) for i in range(8)]
 
 
+def test_stream_shard_properties():
+    """Time split of one long stream (configs[3]): the owned frame ranges tile [0, T), every shard's computed range
+    holds l_harm // 2 halo frames per side (clamped at the stream ends) and its sample range covers exactly them."""
+    from sm_hpss_mtl_b200.dist import stream_shard
+    for (L, n_fft, hop, k, world) in [(57_600_000, 2048, 512, 31, 8), (640_000, 2048, 512, 31, 3), (160_000, 400, 160, 21, 2),
+                                      (16_000, 400, 160, 63, 4)]:
+        T = 1 + (L - n_fft) // hop
+        prev = 0
+        for r in range(world):
+            (t0, t1), (a, b), (s0, s1) = stream_shard(L, n_fft, hop, k, r, world)
+            assert t0 == prev and t1 > t0
+            prev = t1
+            assert a == max(0, t0 - k // 2) and b == min(T, t1 + k // 2)
+            assert s0 == a * hop and s1 == (b - 1) * hop + n_fft and s1 <= L
+            assert 1 + (s1 - s0 - n_fft) // hop == b - a
+        assert prev == T
+    with pytest.raises(ValueError):
+        stream_shard(2048, 2048, 512, 31, 0, 2)
+
+
 def _gloo_worker(rank, world, port, D, q):
     import torch
     import torch.distributed as dist
