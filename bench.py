@@ -66,9 +66,9 @@ def env_int(name, default):
 
 
 def measured_traffic(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/r1_traffic.json), or None."""
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/r2_traffic.json), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             t = json.load(f)[kernel]
         return int(t["read"]) + int(t["write"])
     except Exception:
@@ -474,7 +474,7 @@ def run_gpu(args):
         roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak,
                     "unit": "GB/s", "frac": dom["frac_of_hbm_peak"], "traffic": measured_traffic(dom["kernel"]),
                     "algorithmic_bytes": dom["algorithmic_bytes_per_frame"] * frames, "peak_source": peak_src,
-                    "traffic_source": "profiles/r1_traffic.json (ncu --set full of the same kernels, bytes per launch)",
+                    "traffic_source": "profiles/r2_traffic.json (ncu --set full of the same kernels, bytes per launch)",
                     "note": "the two median kernels are bound by the ALU pipe (half-rate FMNMX selection networks: "
                             "profiles/README.md), HBM is their secondary bound; K1/K3/K3b+K5 are the HBM-side "
                             "stages; per-stage numbers in 'stages'"}

@@ -17,11 +17,22 @@ Pinning status (see DESIGN.md "Oracle"):
   stats) -- pinned: ``tests/golden/make_golden.py`` runs the reference's own
   ``lib/preprocessing.py`` (imported from /root/reference with a ``librosa``
   shim made of the leaf restatements below) and commits its outputs.
-* STFT, softmask, Slaney mel basis, power_to_db -- **parity unpinned** by the
-  reference (librosa is an un-vendored, unpinned dependency that is not
-  installable here and the reference ships no tests or golden vectors); they
-  restate the published librosa (~0.8) algorithm and are cross-checked against
-  independent implementations available in the image (``torch.stft`` in
-  float64, ``torchaudio.functional.melscale_fbanks``,
-  ``transformers.audio_utils``).
+* signal preparation (normalize_signal, removeSilence, the doubling below
+  0.1 s, mix_signals) and get_data_statistics -- pinned: the same script runs
+  the reference's load_and_preprocess_signal / mix_signals and its compiled
+  Cython removeSilence / get_data_statistics; signals, frame markers, sample
+  markers and statistics are reproduced bit for bit by the restatement.
+* STFT, softmask, Slaney mel basis, power_to_db -- **parity unpinned by
+  librosa** (an un-vendored, unpinned dependency that is not installable here;
+  the reference ships no tests or golden vectors).  These four rows -- and
+  ``librosa.feature.rms`` inside the signal preparation, which the golden
+  script shims with the restatement too -- are the ones no librosa run backs.
+  They restate the published librosa (~0.8) algorithm and are pinned by what
+  IS available: analytic known answers that do not pass through this package
+  (tests/test_kat.py: impulse and bin-centred sinusoid spectra, exact rational
+  soft masks, a hand-computed Slaney basis and the 6400 Hz = 42 mel anchor,
+  power_to_db edge values), a whole-pipeline cross-check against
+  ``transformers.audio_utils.spectrogram``, and per-leaf cross-checks against
+  ``torch.stft`` in float64, ``torchaudio.functional.melscale_fbanks`` and
+  ``transformers.audio_utils``.
 """

@@ -1,6 +1,7 @@
 // Micro-benchmark of issue rates on sm_100a: per-SMSP cycles per warp-instruction for a few opcodes and mixes.
 // Development tool (not part of the library): nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipe_bench pipe_bench.cu
 #include <cstdio>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #define ITERS 4096
@@ -44,6 +45,10 @@ __global__ void k(float* out, int* iout, long long* cyc, float seed) {
             if (MODE == 11) { if (i % 3 == 0) ia[i] = ia[i] * ib + ic; else MN(i, 6); }               // 2 FMNMX : 1 IMAD
             if (MODE == 12) { if (i % 4 == 0) ia[i] = ia[i] * ib + ic; else MN(i, 8); }               // 3 FMNMX : 1 IMAD
             if (MODE == 13) ia[i] = ia[i] + ia[(i + 5) % UNROLL] - ia[(i + 9) % UNROLL];               // IADD3
+            if (MODE == 16) ia[i] = __vimin3_s32(ia[i], ia[(i + 5) % UNROLL], ia[(i + 9) % UNROLL]);   // VIMNMX3
+            if (MODE == 17) ia[i] = (int)__vminu2((unsigned)ia[i], (unsigned)ia[(i + 5) % UNROLL]);    // packed u16x2 min
+            if (MODE == 18) { __half2 h = __hmin2(*reinterpret_cast<__half2*>(&ia[i]), *reinterpret_cast<__half2*>(&ia[(i + 5) % UNROLL])); ia[i] = *reinterpret_cast<int*>(&h); }   // HMNMX2
+            if (MODE == 19) ia[i] = (int)min((unsigned)ia[i], (unsigned)ia[(i + 5) % UNROLL]);         // unsigned min
             if (MODE == 14 && (i & 1) == 0) {   // compare-exchange, both FMNMX (2 instr per pair i, i+1)
                 const float lo = fminf(a[i], a[i + 1]), hi = fmaxf(a[i], a[i + 1]); a[i] = lo; a[i + 1] = hi;
             }
@@ -58,6 +63,10 @@ __global__ void k(float* out, int* iout, long long* cyc, float seed) {
             if (MODE == 0) a[i] = fmaf(a[i], c, b);
             if (MODE == 1) MX(i, 3);
             if (MODE == 2) ia[i] = max(ia[i], ia[(i + 3) % UNROLL]);
+            if (MODE == 16) ia[i] = __vimax3_s32(ia[i], ia[(i + 3) % UNROLL], ia[(i + 7) % UNROLL]);
+            if (MODE == 17) ia[i] = (int)__vmaxu2((unsigned)ia[i], (unsigned)ia[(i + 3) % UNROLL]);
+            if (MODE == 18) { __half2 h = __hmax2(*reinterpret_cast<__half2*>(&ia[i]), *reinterpret_cast<__half2*>(&ia[(i + 3) % UNROLL])); ia[i] = *reinterpret_cast<int*>(&h); }
+            if (MODE == 19) ia[i] = (int)max((unsigned)ia[i], (unsigned)ia[(i + 3) % UNROLL]);
             if (MODE == 3) ia[i] = ia[i] * ic + ib;
             if (MODE == 4) ia[i] = __mulhi(ia[i], ic) + ib;
             if (MODE == 5) a[i] = a[i] + c;
@@ -119,6 +128,10 @@ int main() {
         run<1>("FMNMX", w, UNROLL);
         run<10>("FMNMX3 (min3)", w, UNROLL);
         run<2>("IMNMX (int min)", w, UNROLL);
+        run<19>("UMNMX (unsigned min)", w, UNROLL);
+        run<16>("VIMNMX3 (int min3)", w, UNROLL);
+        run<17>("VMNMX u16x2", w, UNROLL);
+        run<18>("HMNMX2 (half2 min)", w, UNROLL);
         run<3>("IMAD", w, UNROLL);
         run<4>("IMAD.HI", w, UNROLL);
         run<6>("FMNMX+FFMA 1:1", w, UNROLL);
