@@ -290,6 +290,10 @@ HPSS_API int hpss_stats_finalize(const double* sum_host, const double* sumsq_hos
 HPSS_API int hpss_scale_data(hpss_ctx* ctx, const hpss_batch* batch, const float* feat_dev, int32_t D,
                              const float* mean_dev, const float* stdev_dev, double eps,
                              double* out_dev, void* stream);
+/* The pure-Python scale_data (lib/preprocessing.py:590-614) on float32 input evaluates (FV - mean) / stdev in float32:
+ * two rounded operations, float32 result -- bit-identical to numpy. */
+HPSS_API int hpss_scale_data_f32(hpss_ctx* ctx, const hpss_batch* batch, const float* feat_dev, int32_t D,
+                                 const float* mean_dev, const float* stdev_dev, float* out_dev, void* stream);
 
 /* ---- N1: get_feature_patches (lib/preprocessing.py:137-292 + tools.pyx:21-38) for one
  * clip-batch: optional per-clip per-row standardisation (sklearn StandardScaler: mean,
@@ -321,6 +325,12 @@ HPSS_API int hpss_patch_offsets(const hpss_batch* batch, int32_t patch_size, int
 HPSS_API int hpss_patch_tensor(hpss_ctx* ctx, const hpss_batch* batch, float* feat_dev, int32_t D, int32_t standardize,
                                int32_t row0, int32_t n_rows, int32_t patch_size, int32_t patch_shift,
                                int32_t time_major, int32_t out_f64, void* out_dev, void* stream);
+/* The same gather for float64 featuregrams -- with frame_level_scaling the generators hand get_feature_patches the
+ * float64 output of the Cython scale_data (Proposed_Work_Results.py:94-95) and no standardisation happens: exact
+ * float64 copies. */
+HPSS_API int hpss_patch_tensor_f64(hpss_ctx* ctx, const hpss_batch* batch, const double* feat_dev, int32_t D,
+                                   int32_t row0, int32_t n_rows, int32_t patch_size, int32_t patch_shift,
+                                   int32_t time_major, double* out_dev, void* stream);
 
 /* get_data_stats drops, per file, the feature rows that hold a NaN or Inf (lib/preprocessing.py:507-508):
  * flags_dev[c * D + d] = 1 when row d of clip c has a non-finite value.  Only needed when hpss_moments reported

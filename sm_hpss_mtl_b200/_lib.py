@@ -97,6 +97,8 @@ PROTOTYPES = {
     "hpss_mix_signals": (C.c_int, [_vp, _vp, _pi64, _vp, _pi64, _vp, _i32, _vp, _vp]),
     "hpss_stats_finalize": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "hpss_scale_data": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _f64, _vp, _vp]),
+    "hpss_scale_data_f32": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "hpss_patch_tensor_f64": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "hpss_row_standardize": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "hpss_num_patches": (_i64, [_i64, _i32, _i32]),
     "hpss_extract_patches": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),

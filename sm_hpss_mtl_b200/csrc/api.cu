@@ -1139,7 +1139,14 @@ int hpss_scale_data(hpss_ctx* ctx, const hpss_batch* batch, const float* feat, i
                     const float* stdev, double eps, double* out, void* stream) {
     if (!ctx || !batch || !feat || !mean || !stdev || !out) { set_error("scale_data: NULL argument"); return HPSS_ERR_INVALID; }
     HPSS_CUDA(cudaSetDevice(ctx->device));
-    return launch_scale(ctx, batch, feat, D, mean, stdev, eps, out, (cudaStream_t)stream);
+    return launch_scale(ctx, batch, feat, D, mean, stdev, eps, out, nullptr, (cudaStream_t)stream);
+}
+
+int hpss_scale_data_f32(hpss_ctx* ctx, const hpss_batch* batch, const float* feat, int32_t D, const float* mean,
+                        const float* stdev, float* out, void* stream) {
+    if (!ctx || !batch || !feat || !mean || !stdev || !out) { set_error("scale_data_f32: NULL argument"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    return launch_scale(ctx, batch, feat, D, mean, stdev, 0.0, nullptr, out, (cudaStream_t)stream);
 }
 
 int hpss_dct_mfcc(hpss_ctx* ctx, const hpss_batch* batch, const float* feat, int32_t rows_per_stream, int32_t n_streams,
@@ -1221,7 +1228,18 @@ int hpss_patch_tensor(hpss_ctx* ctx, const hpss_batch* batch, float* feat, int32
         rc = launch_row_standardize(ctx, batch, feat, D, st);
         if (rc) return rc;
     }
-    return launch_patch_tensor(batch, feat, d, h->back(), D, row0, n_rows, W, shift, time_major, out_f64, out, st);
+    return launch_patch_tensor(batch, feat, 0, d, h->back(), D, row0, n_rows, W, shift, time_major, out_f64, out, st);
+}
+
+int hpss_patch_tensor_f64(hpss_ctx* ctx, const hpss_batch* batch, const double* feat, int32_t D, int32_t row0,
+                          int32_t n_rows, int32_t W, int32_t shift, int32_t time_major, double* out, void* stream) {
+    if (!ctx || !batch || !feat || !out) { set_error("patch_tensor_f64: NULL argument"); return HPSS_ERR_INVALID; }
+    if (D < 1 || row0 < 0 || n_rows < 1 || row0 + n_rows > D || W < 1 || shift < 1) { set_error("patch_tensor_f64: bad shape arguments"); return HPSS_ERR_INVALID; }
+    HPSS_CUDA(cudaSetDevice(ctx->device));
+    const std::vector<int64_t>* h; const int64_t* d;
+    int rc = patch_offsets(const_cast<hpss_batch*>(batch), W, shift, &h, &d);
+    if (rc) return rc;
+    return launch_patch_tensor(batch, feat, 1, d, h->back(), D, row0, n_rows, W, shift, time_major, 1, out, (cudaStream_t)stream);
 }
 
 int hpss_row_nonfinite(hpss_ctx* ctx, const hpss_batch* batch, const float* feat, int32_t D, uint8_t* flags, void* stream) {

@@ -235,13 +235,14 @@ int launch_dct(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int M, int
                cudaStream_t st);
 void build_dct_basis_t(int M, int n_mfcc, int ncols, float* out);
 int launch_scale(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, const float* mean,
-                 const float* stdev, double eps, double* out, cudaStream_t st);
+                 const float* stdev, double eps, double* out, float* out32, cudaStream_t st);
 int launch_row_standardize(hpss_ctx* ctx, const hpss_batch* b, float* feat, int D, cudaStream_t st);
 int launch_patches(const float* feat, int D, int64_t T, int W, int shift, int64_t n_patches, double* out,
                    cudaStream_t st);
 int launch_row_nonfinite(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, uint8_t* flags, cudaStream_t st);
-int launch_patch_tensor(const hpss_batch* b, const float* feat, const int64_t* d_patch_off, int64_t n_patches, int D,
-                        int row0, int n_rows, int W, int shift, int time_major, int out_f64, void* out, cudaStream_t st);
+int launch_patch_tensor(const hpss_batch* b, const void* feat, int in_f64, const int64_t* d_patch_off, int64_t n_patches,
+                        int D, int row0, int n_rows, int W, int shift, int time_major, int out_f64, void* out,
+                        cudaStream_t st);
 int launch_patch_stats(hpss_ctx* ctx, const double* x, int64_t N, int A, int B, int stat, int along_a, double* out,
                        cudaStream_t st);
 

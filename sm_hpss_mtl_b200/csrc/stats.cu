@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kThreads)
 scale_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_off,
              const int32_t* __restrict__ block_clip, int64_t total_frames,
              int D, const float* __restrict__ mean, const float* __restrict__ stdev, double eps,
-             double* __restrict__ out) {
+             double* __restrict__ out, float* __restrict__ out32) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t gf = (int64_t)blockIdx.x * 32 + lane;
     if (gf >= total_frames) return;
@@ -287,7 +287,10 @@ scale_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_o
     const int64_t base = (int64_t)D * fo + (gf - fo);
     for (int d = warp; d < D; d += kWarps) {
         const int64_t g = base + (int64_t)d * T;
-        out[g] = ((double)__ldg(feat + g) - (double)__ldg(mean + d)) / ((double)__ldg(stdev + d) + eps);
+        if (out32)      // numpy's float32 evaluation of (FV - mean) / stdev: two rounded float32 operations (:612-613)
+            out32[g] = __fdiv_rn(__fsub_rn(__ldg(feat + g), __ldg(mean + d)), __ldg(stdev + d));
+        else
+            out[g] = ((double)__ldg(feat + g) - (double)__ldg(mean + d)) / ((double)__ldg(stdev + d) + eps);
     }
 }
 
@@ -367,12 +370,12 @@ row_nonfinite_kernel(const float* __restrict__ feat, const int64_t* __restrict__
 // out[(patch, w, r)] (the transposed layout the TCNs take, Proposed_Work_Results.py:235-236).  One CTA = one 32 x 32
 // (row, frame) tile of one patch: reads are coalesced along frames, writes along the innermost output axis (through a
 // shared-memory transpose when that is the row axis).
-template <typename OUT, bool TIME_MAJOR>
+template <typename IN, typename OUT, bool TIME_MAJOR>
 __global__ void __launch_bounds__(kThreads)
-patch_tensor_kernel(const float* __restrict__ feat, const int64_t* __restrict__ frame_off,
+patch_tensor_kernel(const IN* __restrict__ feat, const int64_t* __restrict__ frame_off,
                     const int64_t* __restrict__ patch_off, int n_clips, int D, int row0, int n_rows, int W, int shift,
                     OUT* __restrict__ out) {
-    __shared__ float tile[32][33];
+    __shared__ OUT tile[32][33];
     __shared__ int s_clip;
     const int64_t p = blockIdx.x;                                  // patches on the x axis (no 65535 limit)
     if (threadIdx.x == 0) s_clip = find_clip(patch_off, n_clips, p);
@@ -381,7 +384,7 @@ patch_tensor_kernel(const float* __restrict__ feat, const int64_t* __restrict__ 
     const int64_t fo = __ldg(frame_off + c);
     const int T = (int)(__ldg(frame_off + c + 1) - fo);
     const int64_t start = (p - __ldg(patch_off + c)) * shift;
-    const float* base = feat + (int64_t)D * fo + (int64_t)row0 * T;
+    const IN* base = feat + (int64_t)D * fo + (int64_t)row0 * T;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
     const int w0 = blockIdx.z * 32, r0 = blockIdx.y * 32;
     OUT* op = out + (int64_t)p * n_rows * W;
@@ -390,10 +393,10 @@ patch_tensor_kernel(const float* __restrict__ feat, const int64_t* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = r0 + ty + 8 * i;
-        float v = 0.f;
-        if (r < n_rows && w < W) v = __ldg(base + (int64_t)r * T + t);
+        OUT v = (OUT)0;
+        if (r < n_rows && w < W) v = (OUT)__ldg(base + (int64_t)r * T + t);
         if (TIME_MAJOR) tile[ty + 8 * i][tx] = v;
-        else if (r < n_rows && w < W) op[(int64_t)r * W + w] = (OUT)v;
+        else if (r < n_rows && w < W) op[(int64_t)r * W + w] = v;
     }
     if (TIME_MAJOR) {
         __syncthreads();
@@ -401,7 +404,7 @@ patch_tensor_kernel(const float* __restrict__ feat, const int64_t* __restrict__ 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int ww = w0 + ty + 8 * i;
-            if (r < n_rows && ww < W) op[(int64_t)ww * n_rows + r] = (OUT)tile[tx][ty + 8 * i];
+            if (r < n_rows && ww < W) op[(int64_t)ww * n_rows + r] = tile[tx][ty + 8 * i];
         }
     }
 }
@@ -459,14 +462,18 @@ int launch_row_nonfinite(hpss_ctx* ctx, const hpss_batch* b, const float* feat, 
     return HPSS_OK;
 }
 
-int launch_patch_tensor(const hpss_batch* b, const float* feat, const int64_t* d_patch_off, int64_t n_patches, int D,
-                        int row0, int n_rows, int W, int shift, int time_major, int out_f64, void* out, cudaStream_t st) {
+int launch_patch_tensor(const hpss_batch* b, const void* feat, int in_f64, const int64_t* d_patch_off, int64_t n_patches,
+                        int D, int row0, int n_rows, int W, int shift, int time_major, int out_f64, void* out,
+                        cudaStream_t st) {
     if (n_patches == 0) return HPSS_OK;
     if (n_patches > 0x7fffffffLL) { set_error("patch_tensor: too many patches"); return HPSS_ERR_UNSUPPORTED; }
     dim3 grid((unsigned)n_patches, (unsigned)((n_rows + 31) / 32), (unsigned)((W + 31) / 32));
-#define HPSS_PT(OUT, TM) patch_tensor_kernel<OUT, TM><<<grid, kThreads, 0, st>>>(feat, b->d_frame_off, d_patch_off, b->n_clips, D, row0, n_rows, W, shift, (OUT*)out)
-    if (out_f64) { if (time_major) HPSS_PT(double, true); else HPSS_PT(double, false); }
-    else { if (time_major) HPSS_PT(float, true); else HPSS_PT(float, false); }
+#define HPSS_PT(IN, OUT, TM) patch_tensor_kernel<IN, OUT, TM><<<grid, kThreads, 0, st>>>((const IN*)feat, b->d_frame_off, d_patch_off, b->n_clips, D, row0, n_rows, W, shift, (OUT*)out)
+    if (in_f64) {       // float64 featuregrams (the output of the Cython scale_data): float64 patches, exact copies
+        if (!out_f64) { set_error("patch_tensor: float64 input needs float64 output"); return HPSS_ERR_INVALID; }
+        if (time_major) HPSS_PT(double, double, true); else HPSS_PT(double, double, false);
+    } else if (out_f64) { if (time_major) HPSS_PT(float, double, true); else HPSS_PT(float, double, false); }
+    else { if (time_major) HPSS_PT(float, float, true); else HPSS_PT(float, float, false); }
 #undef HPSS_PT
     HPSS_LAUNCHED("patch_tensor_kernel");
     return HPSS_OK;
@@ -553,12 +560,12 @@ int launch_topdb_moments(hpss_ctx* ctx, const hpss_batch* b, float* feat, int ro
 }
 
 int launch_scale(hpss_ctx* ctx, const hpss_batch* b, const float* feat, int D, const float* mean,
-                 const float* stdev, double eps, double* out, cudaStream_t st) {
+                 const float* stdev, double eps, double* out, float* out32, cudaStream_t st) {
     (void)ctx;
     const int64_t total = b->frame_off[b->n_clips];
     if (total == 0) return HPSS_OK;
     scale_kernel<<<(unsigned)((total + 31) / 32), kThreads, 0, st>>>(feat, b->d_frame_off, b->d_block_clip, total, D, mean,
-                                                                     stdev, eps, out);
+                                                                     stdev, eps, out, out32);
     HPSS_LAUNCHED("scale_kernel");
     return HPSS_OK;
 }

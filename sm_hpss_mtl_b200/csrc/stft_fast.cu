@@ -45,7 +45,10 @@ struct FastCfg {
 #ifndef HPSS_K1_TT400
 #define HPSS_K1_TT400 16            // frames per tile of the 400/160 configuration (16 or 32; 32 measured 5 % slower)
 #endif
-    static constexpr int TT = (NFFT == 400) ? HPSS_K1_TT400 : 16;       // frames per tile = lanes per group
+#ifndef HPSS_K1_TT_BIG
+#define HPSS_K1_TT_BIG 8            // frames per tile at n_fft = 2048: half the shared memory, two CTAs per SM instead of
+#endif                              // one (0.516 -> 0.479 ms on 64 x 60 s; at n_fft = 1024 8-frame tiles are slower: 0.38 -> 0.49 ms)
+    static constexpr int TT = (NFFT == 400) ? HPSS_K1_TT400 : (NFFT >= 2048 ? HPSS_K1_TT_BIG : 16);   // frames per tile = lanes per group
     static constexpr int ZS = N2 | 1;                                   // float2 stride between frames
     static constexpr int PAD = ((HOP / 2) % 2 == 0) ? 2 : 0;            // (HOP + PAD) / 2 odd
     static constexpr int HOPP = HOP + PAD;

@@ -508,6 +508,15 @@ def scale_data(batch: Batch, feat: torch.Tensor, D: int, mean: torch.Tensor, std
     return out
 
 
+def scale_data_f32(batch: Batch, feat: torch.Tensor, D: int, mean: torch.Tensor, stdev: torch.Tensor) -> torch.Tensor:
+    """numpy's float32 evaluation of (FV - mean) / stdev (lib/preprocessing.py:590-614), bit-identical."""
+    out = torch.empty(feat.numel(), dtype=torch.float32, device=feat.device)
+    check(batch.lib.hpss_scale_data_f32(batch.ctx.handle, batch.handle, _dev_ptr(feat, torch.float32, "feat"), int(D),
+                                        _dev_ptr(mean, torch.float32, "mean"), _dev_ptr(stdev, torch.float32, "stdev"),
+                                        _dev_ptr(out), _stream_ptr()))
+    return out
+
+
 def row_standardize(batch: Batch, feat: torch.Tensor, D: int) -> torch.Tensor:
     check(batch.lib.hpss_row_standardize(batch.ctx.handle, batch.handle, _dev_ptr(feat, torch.float32, "feat"), int(D),
                                          _stream_ptr()))
@@ -554,6 +563,13 @@ def patch_tensor(batch: Batch, feat: torch.Tensor, D: int, patch_size: int, patc
     if dtype not in (torch.float32, torch.float64):
         raise ValueError("dtype must be torch.float32 or torch.float64")
     out = torch.empty(shape, dtype=dtype, device=feat.device)
+    if feat.dtype == torch.float64:                       # frame-level-scaled float64 featuregrams: exact float64 gather
+        if standardize or dtype != torch.float64:
+            raise ValueError("float64 featuregrams are gathered as they are (no standardisation, float64 output)")
+        check(batch.lib.hpss_patch_tensor_f64(batch.ctx.handle, batch.handle, _dev_ptr(feat, torch.float64, "feat"), int(D),
+                                              int(row0), int(n_rows), int(patch_size), int(patch_shift),
+                                              int(bool(time_major)), _dev_ptr(out), _stream_ptr()))
+        return out
     check(batch.lib.hpss_patch_tensor(batch.ctx.handle, batch.handle, _dev_ptr(feat, torch.float32, "feat"), int(D),
                                       int(bool(standardize)), int(row0), int(n_rows), int(patch_size), int(patch_shift),
                                       int(bool(time_major)), int(dtype == torch.float64), _dev_ptr(out), _stream_ptr()))

@@ -433,7 +433,10 @@ def get_feature_patches(PARAMS, FV, patch_size, patch_shift, featName):
     rows = _patch_rows(featName)
     ctx = engine.get_context()
     D, T = FV.shape
-    feat = torch.from_numpy(np.ascontiguousarray(FV, dtype=np.float32)).cuda()
+    # with frame_level_scaling the generators pass the float64 output of the Cython scale_data and nothing is
+    # standardised: those values are gathered exactly; otherwise float32 featuregrams, as get_featuregram returns them
+    keep64 = bool(PARAMS['frame_level_scaling']) and FV.dtype == np.float64
+    feat = torch.from_numpy(np.ascontiguousarray(FV, dtype=np.float64 if keep64 else np.float32)).cuda()
     batch = engine.Batch(ctx, clip_frames=[T])
     patches = engine.patch_tensor(batch, feat.view(-1), D, patch_size, patch_shift,
                                   standardize=not PARAMS['frame_level_scaling'], rows=rows, time_major=False,
@@ -459,8 +462,23 @@ def get_data_statistics(FV, stat_type='skew', axis=0):
 
 # ============================================================================ global statistics
 def scale_data(FV, mean, stdev):
-    """lib/preprocessing.py:590-614 ((x - mean) / stdev, numpy promotion of the inputs)."""
-    return _scale(FV, mean, stdev, 0.0, np.result_type(np.asarray(FV).dtype, np.asarray(mean).dtype))
+    """lib/preprocessing.py:590-614 ((x - mean) / stdev, numpy promotion of the inputs: float32 arithmetic -- two
+    rounded operations, bit-identical to numpy -- when everything is float32, float64 otherwise)."""
+    import torch
+    from . import engine
+    dt = np.result_type(np.asarray(FV).dtype, np.asarray(mean).dtype, np.asarray(stdev).dtype)
+    if dt != np.float32:
+        return _scale(FV, mean, stdev, 0.0, dt)
+    FV = np.ascontiguousarray(FV, dtype=np.float32)
+    D, T = FV.shape
+    ctx = engine.get_context()
+    batch = engine.Batch(ctx, clip_frames=[T])
+    out = engine.scale_data_f32(batch, torch.from_numpy(FV.ravel()).cuda(),
+                                D, torch.from_numpy(np.ascontiguousarray(mean, dtype=np.float32)).cuda(),
+                                torch.from_numpy(np.ascontiguousarray(stdev, dtype=np.float32)).cuda())
+    res = out.cpu().numpy().reshape(D, T)
+    batch.close()
+    return res
 
 
 def cscale_data(FV, mean, stdev):

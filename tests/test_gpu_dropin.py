@@ -97,7 +97,13 @@ def test_get_data_stats_matches_reference(ctx, golden, loader, tmp_path):
     assert np.allclose(std, golden["stats:std"], rtol=1e-4, atol=1e-3)
     FV = golden["fv:speech:LogMelHarmPercSpec"]
     assert np.allclose(pp.cscale_data(FV, golden["stats:mean"], golden["stats:std"]), golden["scaled:cy"], rtol=1e-12)
-    assert np.allclose(pp.scale_data(FV, golden["stats:mean"], golden["stats:std"]), golden["scaled:py"], rtol=1e-6)
+    py = pp.scale_data(FV, golden["stats:mean"], golden["stats:std"])
+    assert py.dtype == np.float32 and np.array_equal(py, golden["scaled:py"])      # numpy's float32 evaluation, bit for bit
+    # frame_level_scaling: the generators hand the float64 output of the Cython scale_data to get_feature_patches
+    P = dict(PARAMS, Model="Lemaire_et_al_MTL", frame_level_scaling=True)
+    cy = golden["scaled:cy"]
+    got = pp.get_feature_patches(P, cy, 49, 24, "LogMelHarmPercSpec")
+    assert got.dtype == np.float64 and np.array_equal(got, po.extract_patches(cy, 49, 24))
 
 
 def test_librosa_compat_surface(ctx):

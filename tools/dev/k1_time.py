@@ -8,9 +8,10 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from sm_hpss_mtl_b200 import engine, synth  # noqa: E402
 
-n, L = 4096, 16000
+n, L = int(os.environ.get("N", 4096)), int(os.environ.get("L", 16000))
+NFFT, HOP = int(os.environ.get("NFFT", 400)), int(os.environ.get("HOP", 160))
 ctx = engine.get_context(0)
-batch = engine.Batch(ctx, clip_lengths=[L] * n, n_fft=400, hop_length=160)
+batch = engine.Batch(ctx, clip_lengths=[L] * n, n_fft=NFFT, hop_length=HOP)
 wave = torch.from_numpy(synth.synth_batch_fast(n, L).ravel()).cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 reps = int(os.environ.get("REPS", 20))
@@ -19,7 +20,7 @@ for it in range(reps + 3):
     flush.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    S = engine.stft_mag(batch, wave, 400, 400, 160)
+    S = engine.stft_mag(batch, wave, NFFT, min(NFFT, int(os.environ.get("WIN", NFFT))), HOP)
     e1.record()
     torch.cuda.synchronize()
     if it >= 3:
