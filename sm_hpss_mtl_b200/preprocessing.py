@@ -625,6 +625,15 @@ def _stat_jobs(PARAMS, files):
     return jobs
 
 
+def _shard_jobs(jobs, rank, world):
+    """Contiguous slice of the job list for one rank (every job lands on exactly one rank; the file lengths are not
+    known before decoding, so the cut is by count)."""
+    if world <= 1:
+        return jobs
+    per = (len(jobs) + world - 1) // world
+    return jobs[rank * per:(rank + 1) * per]
+
+
 def get_data_stats(PARAMS, files, loader=None, group=None, shard=True, batch_samples: int = 1 << 27):
     """Same signature and return value as lib/preprocessing.py:461-586: (mean f32[D], stdev f32[D], nMuFrames,
     nSpFrames, nSpMuFrames).  Every file of every class goes through the feature cache (``.npy`` under
@@ -648,9 +657,7 @@ def get_data_stats(PARAMS, files, loader=None, group=None, shard=True, batch_sam
             rank, world = dist.get_rank(group), dist.get_world_size(group)
     except Exception:
         pass
-    if world > 1:
-        per = (len(jobs) + world - 1) // world
-        jobs = jobs[rank * per:(rank + 1) * per]
+    jobs = _shard_jobs(jobs, rank, world)
     ctx = engine.get_context()
     mom = _Moments(ctx, len(names))
     loader = loader or load_pcm

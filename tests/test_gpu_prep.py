@@ -139,6 +139,77 @@ def test_prep_long_clip_many_chunks(ctx):
     assert np.abs(out[x.size:] - want2).max() <= SIG_TOL
 
 
+@pytest.mark.parametrize("Tw,Ts", [(25, 10), (20, 10), (32, 8), (64, 16)])
+def test_prep_other_frame_sizes_and_edge_clips(ctx, Tw, Ts):
+    """Frame sizes other than 25 / 10 ms (win 320 / 512 / 1024, hop 128 / 160 / 256), clips of 2 .. a few hundred samples
+    (shorter than one frame: the reflect padding wraps several times; all below 0.1 s: doubled 1 .. 10 times), a
+    clip that is silent except for one burst, and a constant clip (peak 0: the reference divides by zero -> NaN)."""
+    rng = np.random.default_rng(Tw * 100 + Ts)
+    clips = [gappy_clip(900 + i, n, g) for i, (n, g) in enumerate([(30000, 4), (16000, 2), (50000, 6)])]
+    clips += [rng.standard_normal(n).astype(np.float32) for n in (2, 3, 17, 161, 399, 1599)]
+    burst = np.full(24000, 1e-6, np.float32) * rng.standard_normal(24000).astype(np.float32)
+    burst[9000:9800] = rng.standard_normal(800).astype(np.float32)
+    clips.append(burst)
+    out, olen, fm, sm, ns = pp.prepare_signals_device(ctx, clips, Tw, Ts, markers=True)
+    engine.ctx_check(ctx)
+    out, fm, sm = out.cpu().numpy(), fm.cpu().numpy(), sm.cpu().numpy()
+    o = f = s = 0
+    for i, x in enumerate(clips):
+        want, smark, fmark, _ = po.load_and_preprocess_signal(x, Tw, Ts, details=True)
+        assert olen[i] == want.size and want.size >= 1600
+        assert np.array_equal(fm[f:f + fmark.size], fmark), (i, x.size)
+        assert np.array_equal(sm[s:s + x.size], smark), (i, x.size)
+        # a mean over 2 .. 17 float32 samples carries a relative rounding error of ~6e-8 in numpy, which the two
+        # normalisations turn into a few ulp of the result: 1e-6 for those, the usual 2e-7 otherwise
+        tol = SIG_TOL if x.size >= 100 else 1e-6
+        assert np.abs(out[o:o + want.size] - want).max() <= tol, (i, x.size)
+        o += want.size; f += fmark.size; s += x.size
+    # constant clip: mean-subtracted signal is all zero, peak 0 -> 0 / 0 like numpy (NaN everywhere), reported by the features
+    const = np.full(4000, 0.25, np.float32)
+    got, _ = pp.prepare_signals_device(ctx, [const], Tw, Ts)
+    with np.errstate(all="ignore"):
+        want = po.load_and_preprocess_signal(const, Tw, Ts)
+    assert np.isnan(want).all() and bool(torch.isnan(got).all())
+
+
+def test_pipeline_ragged_prepare_features_and_errors(ctx):
+    """hpss_pipeline with ragged decoded files, preparation, features AND moments in one run; argument checking;
+    non-finite PCM is reported by the run itself."""
+    lens = [1000, 52000, 16000, 700, 33333, 16000, 120000, 2500]
+    clips = [gappy_clip(700 + i, n, 2) for i, n in enumerate(lens)]
+    cls = [i % 2 for i in range(len(lens))]
+    prm = engine.make_params(n_fft=400, win_length=400, hop_length=160, l_harm=21, l_perc=11, n_mels=40)
+    pl = engine.Pipeline(ctx, lens, prm, pcm_dtype=np.float32, prepare=True, n_chunks=3)
+    pcm = np.concatenate(clips)
+    feat, mom = pl.run(pcm, clip_class=cls, n_classes=2)
+    D = pl.rows
+    for c, x in enumerate(clips):
+        y = po.load_and_preprocess_signal(x, 25, 10)
+        want = po.featuregram(y, 16000, 25, 10, 21, 11, 400, 40, "LogMelHarmPercSpec")
+        a, b = D * int(pl.frame_offsets[c]), D * int(pl.frame_offsets[c + 1])
+        got = feat[a:b].reshape(D, -1)
+        assert got.shape == want.shape and rel_l2(got, want) < 1e-4, c
+    counts = mom[2 * D + D:2 * D + D + 2]
+    assert [int(v) for v in counts] == [int(sum(pl.frame_offsets[c + 1] - pl.frame_offsets[c] for c in range(len(lens)) if cls[c] == k))
+                                        for k in (0, 1)]
+    with pytest.raises(ValueError):
+        pl.run(pcm[:-1])
+    with pytest.raises(ValueError):
+        pl.run(pcm, clip_class=cls[:-1], n_classes=2)
+    with pytest.raises(_lib.HpssError):
+        pl.run(pcm, clip_class=[5] * len(lens), n_classes=2)              # class outside [0, n_classes)
+    bad = pcm.copy()
+    bad[60000] = np.inf
+    with pytest.raises(_lib.ParameterError, match="not finite"):
+        pl.run(bad)
+    pl.run(pcm)                                                           # the status word was cleared
+    pl.close()
+    with pytest.raises(_lib.ParameterError):                              # n_fft larger than a (prepared) clip: like librosa.stft
+        engine.Pipeline(ctx, [100], engine.make_params(n_fft=2048, win_length=2048, hop_length=512), prepare=True)
+    with pytest.raises(_lib.HpssError):                                   # 16-bit PCM needs the preparation
+        engine.Pipeline(ctx, lens, prm, pcm_dtype=np.int16, prepare=False)
+
+
 def test_nonfinite_audio_is_reported(ctx, audio):
     x = audio["/d/speech/sp1.wav"].copy()
     x[5000] = np.nan

@@ -214,6 +214,15 @@ def test_shard_clips_properties():
     assert shard_clips([16000] * 4096, 8) == [(i * 512, (i + 1) * 512) for i in range(8)]
 
 
+def test_stat_jobs_sharding_covers_every_file_once():
+    from sm_hpss_mtl_b200.preprocessing import _shard_jobs
+    for n, world in [(1086, 8), (7, 8), (0, 4), (100, 3), (5, 1)]:
+        jobs = list(range(n))
+        parts = [_shard_jobs(jobs, r, world) for r in range(world)]
+        assert sum(parts, []) == jobs                                        # order kept, nothing lost or repeated
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= max(1, -(-n // world))
+
+
 def test_stream_shard_properties():
     """Time split of one long stream (configs[3]): the owned frame ranges tile [0, T), every shard's computed range
     holds l_harm // 2 halo frames per side (clamped at the stream ends) and its sample range covers exactly them."""
