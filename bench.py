@@ -434,7 +434,29 @@ def run_gpu(args):
         for _ in range(10):
             pp.featuregram_batch(sigs, CFG["fs"], P, 400, 120, "LogMelHarmPercSpec")
         t_64 = (time.perf_counter() - t0) / 10
+        # N1, device resident: the features of the bench batch (already on the device) -> model-ready patch tensor
+        # (per-file StandardScaler in place, tiling of the 98-frame clips, gather, TCN transpose), float32
+        n1 = {}
+        Pn1 = dict(P, Model="Lemaire_et_al_MTL")
+        for (W, sh) in ((68, 68), (249, 24)):
+            ts = []
+            for it in range(6):
+                engine.featuregram(batch, wave, prm, out=out)               # fresh features (standardised in place below)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                pt = pp.feature_patches_device(Pn1, batch, out, D, W, sh, "LogMelHarmPercSpec")
+                e1.record()
+                torch.cuda.synchronize()
+                if it:
+                    ts.append(e0.elapsed_time(e1))
+                nb = pt.numel() * 4
+                shp = list(pt.shape)
+                del pt
+            ms = statistics.median(ts)
+            n1[f"W{W}_shift{sh}"] = {"ms": round(ms, 4), "tensor": shp, "out_GBps": round(nb / ms / 1e6, 1),
+                                     "in_plus_out_GBps": round((nb + 2 * out.numel() * 4) / ms / 1e6, 1)}
         dropin = {"get_featuregram_one_10s_file_ms": round(1e3 * t_one, 3), "shape": list(fv.shape),
+                  "feature_patches_device": n1,
                   "includes": "decoded int16 PCM -> upload -> prep (N2) -> features (k = 21/11) -> download, wall clock",
                   "featuregram_batch_64x1s_ms": round(1e3 * t_64, 3),
                   "cpu_oracle_one_10s_file_ms_1core": None if cpu_base is None else round(cpu_base.get("one_10s_clip_ms_1core", 0.0), 1)}

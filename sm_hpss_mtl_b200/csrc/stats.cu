@@ -326,6 +326,47 @@ row_standardize_kernel(float* __restrict__ feat, const int64_t* __restrict__ fra
     }
 }
 
+// The same for lines that fit the registers of a warp (T <= 32 * NV): every value is loaded once, mean, variance and
+// the update come from registers (same per-lane summation order as the kernel above: bit-identical results), one
+// read and one write of the features instead of three reads and one write.
+template <int NV>
+__global__ void __launch_bounds__(kThreads)
+row_standardize_cached_kernel(float* __restrict__ feat, const int64_t* __restrict__ frame_off, int n_clips, int D) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_lines = (int64_t)n_clips * D;
+    for (int64_t line = (int64_t)blockIdx.x * kWarps + warp; line < n_lines; line += (int64_t)gridDim.x * kWarps) {
+        const int c = (int)(line / D);
+        const int d = (int)(line - (int64_t)c * D);
+        const int64_t fo = __ldg(frame_off + c);
+        const int T = (int)(__ldg(frame_off + c + 1) - fo);
+        if (T <= 0) continue;
+        float* x = feat + (int64_t)D * fo + (int64_t)d * T;
+        float v[NV];
+#pragma unroll
+        for (int u = 0; u < NV; ++u) v[u] = (lane + 32 * u < T) ? x[lane + 32 * u] : 0.f;
+        double s = 0.0;
+#pragma unroll
+        for (int u = 0; u < NV; ++u) if (lane + 32 * u < T) s += (double)v[u];
+        const double mean = warp_sum(s) / (double)T;
+        double q = 0.0;
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+            if (lane + 32 * u < T) {
+                const double dlt = (double)v[u] - mean;
+                q += dlt * dlt;
+            }
+        }
+        const double var = warp_sum(q) / (double)T;
+        const double eps = 2.220446049250313e-16;
+        const double ub = (double)T * eps * var + ((double)T * mean * eps) * ((double)T * mean * eps);
+        const double scale = (var <= ub) ? 1.0 : sqrt(var);
+        const float mean32 = (float)mean, scale32 = (float)scale;
+#pragma unroll
+        for (int u = 0; u < NV; ++u)
+            if (lane + 32 * u < T) x[lane + 32 * u] = __fdiv_rn(__fsub_rn(v[u], mean32), scale32);
+    }
+}
+
 // patches[p, d, w] = feat[d, start_p + w] as float64 (tools.pyx:21-38)
 __global__ void __launch_bounds__(kThreads)
 patches_kernel(const float* __restrict__ feat, int D, int64_t T, int W, int shift, int64_t n_patches,
@@ -386,25 +427,35 @@ patch_tensor_kernel(const IN* __restrict__ feat, const int64_t* __restrict__ fra
     const int64_t start = (p - __ldg(patch_off + c)) * shift;
     const IN* base = feat + (int64_t)D * fo + (int64_t)row0 * T;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
-    const int w0 = blockIdx.z * 32, r0 = blockIdx.y * 32;
+    const int r0 = blockIdx.y * 32;                                // one CTA = 32 rows x the whole patch width
     OUT* op = out + (int64_t)p * n_rows * W;
-    const int w = w0 + tx;
-    const int t = w < W ? (int)((start + w) % T) : 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = r0 + ty + 8 * i;
-        OUT v = (OUT)0;
-        if (r < n_rows && w < W) v = (OUT)__ldg(base + (int64_t)r * T + t);
-        if (TIME_MAJOR) tile[ty + 8 * i][tx] = v;
-        else if (r < n_rows && w < W) op[(int64_t)r * W + w] = v;
-    }
-    if (TIME_MAJOR) {
-        __syncthreads();
-        const int r = r0 + tx;
+    for (int w0 = 0; w0 < W; w0 += 32) {
+        const int w = w0 + tx;
+        const int t = w < W ? (int)((start + w) % T) : 0;
+        OUT v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int ww = w0 + ty + 8 * i;
-            if (r < n_rows && ww < W) op[(int64_t)ww * n_rows + r] = tile[tx][ty + 8 * i];
+            const int r = r0 + ty + 8 * i;
+            v[i] = (OUT)0;
+            if (r < n_rows && w < W) v[i] = (OUT)__ldg(base + (int64_t)r * T + t);
+        }
+        if (!TIME_MAJOR) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r0 + ty + 8 * i;
+                if (r < n_rows && w < W) op[(int64_t)r * W + w] = v[i];
+            }
+        } else {
+            if (w0) __syncthreads();                               // the previous tile has been read
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tile[ty + 8 * i][tx] = v[i];
+            __syncthreads();
+            const int r = r0 + tx;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ww = w0 + ty + 8 * i;
+                if (r < n_rows && ww < W) op[(int64_t)ww * n_rows + r] = tile[tx][ty + 8 * i];
+            }
         }
     }
 }
@@ -467,7 +518,7 @@ int launch_patch_tensor(const hpss_batch* b, const void* feat, int in_f64, const
                         cudaStream_t st) {
     if (n_patches == 0) return HPSS_OK;
     if (n_patches > 0x7fffffffLL) { set_error("patch_tensor: too many patches"); return HPSS_ERR_UNSUPPORTED; }
-    dim3 grid((unsigned)n_patches, (unsigned)((n_rows + 31) / 32), (unsigned)((W + 31) / 32));
+    dim3 grid((unsigned)n_patches, (unsigned)((n_rows + 31) / 32), 1);
 #define HPSS_PT(IN, OUT, TM) patch_tensor_kernel<IN, OUT, TM><<<grid, kThreads, 0, st>>>((const IN*)feat, b->d_frame_off, d_patch_off, b->n_clips, D, row0, n_rows, W, shift, (OUT*)out)
     if (in_f64) {       // float64 featuregrams (the output of the Cython scale_data): float64 patches, exact copies
         if (!out_f64) { set_error("patch_tensor: float64 input needs float64 output"); return HPSS_ERR_INVALID; }
@@ -574,6 +625,14 @@ int launch_row_standardize(hpss_ctx* ctx, const hpss_batch* b, float* feat, int 
     const int64_t n_lines = (int64_t)b->n_clips * D;
     if (n_lines == 0) return HPSS_OK;
     int64_t grid = (n_lines + kWarps - 1) / kWarps;
+    if (b->max_frames <= 1024) {                      // lines that fit a warp's registers: one read, one write
+        const int64_t cap = (int64_t)ctx->sm_count * 64;
+        if (grid > cap) grid = cap;
+        if (b->max_frames <= 128) row_standardize_cached_kernel<4><<<(unsigned)grid, kThreads, 0, st>>>(feat, b->d_frame_off, b->n_clips, D);
+        else row_standardize_cached_kernel<32><<<(unsigned)grid, kThreads, 0, st>>>(feat, b->d_frame_off, b->n_clips, D);
+        HPSS_LAUNCHED("row_standardize_cached_kernel");
+        return HPSS_OK;
+    }
     const int64_t cap = (int64_t)ctx->sm_count * 8;
     if (grid > cap) grid = cap;
     row_standardize_kernel<<<(unsigned)grid, kThreads, 0, st>>>(feat, b->d_frame_off, b->n_clips, D);
