@@ -447,6 +447,13 @@ def get_feature_patches(PARAMS, FV, patch_size, patch_shift, featName):
     return patches
 
 
+def get_feature_patches_dafx(PARAMS, FV, patch_size, patch_shift, featName):
+    """The long-form script's copy (DAFx12_Speech_Music_Detection_B3_MTL_v2.py:257-292): no standardisation inside (the
+    script standardises every file before cutting it into blocks, :613-626), float32 patches."""
+    return get_feature_patches(dict(PARAMS, frame_level_scaling=True), np.asarray(FV, dtype=np.float32), patch_size,
+                               patch_shift, featName).astype(np.float32)
+
+
 def get_data_statistics(FV, stat_type='skew', axis=0):
     """lib/cython_impl/tools.pyx:169-211 on the GPU: per-patch mean / variance / skew / kurtosis vectors of a
     (N, f, t) patch array along axis 0 (over f -> (N, t)) or 1 (over t -> (N, f))."""

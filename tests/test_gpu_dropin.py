@@ -76,6 +76,14 @@ def test_get_feature_patches_matches_reference(ctx, golden, model, fn, W, sh):
     assert np.array_equal(FV, before)        # unlike the reference we do not mutate the caller's array
 
 
+def test_get_feature_patches_dafx_variant(ctx, golden):
+    """DAFx12 copy: patches of an already standardised featuregram, float32, stride 1."""
+    FV = po._standard_scale_rows(golden["fv:speech:LogMelHarmPercSpec"])
+    got = pp.get_feature_patches_dafx(dict(PARAMS, Model="Lemaire_et_al_MTL"), FV, 99, 1, "LogMelHarmPercSpec")
+    want = po.extract_patches(FV, 99, 1).astype(np.float32)
+    assert got.dtype == np.float32 and got.shape == want.shape == (FV.shape[1] - 98, 80, 99) and np.array_equal(got, want)
+
+
 def test_get_feature_patches_spec_and_fls(ctx, golden):
     got = pp.get_feature_patches(dict(PARAMS, Model="Doukhan_et_al_MTL"), golden["fv:speech:Spec"], 21, 21, "Spec")
     assert np.allclose(got, golden["patch:Doukhan_et_al_MTL:Spec:21:21"], rtol=0, atol=4e-6)
