@@ -209,6 +209,24 @@ struct FillCache {   // time axis, uniform batch: reflected source offsets of th
     int off[kChunks];
 };
 
+// rows r0, r0 + kLoaderWarps, ... < re of one run of equal-length rows: NF whole chunks of 32 positions + one partial
+// chunk per row.  Byte address = row + 4 * offset as ONE IMAD.WIDE on the FMA pipe (the multiplier is a run-time 4,
+// so the compiler cannot turn it into the two-instruction LEA pair on the ALU pipe, which this kernel saturates).
+template <int NF>
+__device__ __forceinline__ void fill_rows(const float* rowp, uint32_t drow, int64_t sstep, uint32_t dstep, int r0, int re,
+                                          const int (&off)[FillCache::kChunks], uint32_t four, bool tail) {
+#pragma unroll 2
+    for (int r = r0; r < re; r += kLoaderWarps, drow += dstep, rowp += sstep) {
+#pragma unroll
+        for (int q = 0; q < NF; ++q)
+            cp_async4(drow + 128u * q, reinterpret_cast<const float*>(reinterpret_cast<const char*>(rowp) +
+                                                                     (uint64_t)(uint32_t)off[q] * four));
+        if (tail)
+            cp_async4(drow + 128u * NF, reinterpret_cast<const float*>(reinterpret_cast<const char*>(rowp) +
+                                                                      (uint64_t)(uint32_t)off[NF < FillCache::kChunks ? NF : 0] * four));
+    }
+}
+
 template <bool TIME_AXIS>
 __device__ __forceinline__ void tile_fill_async(uint32_t sm_base, const float* __restrict__ S, const LineInfo& li,
                                                 int lane, int lw, int p0, int halo, int span, int lstride, FillCache (&fc)[2]) {
@@ -246,17 +264,18 @@ __device__ __forceinline__ void tile_fill_async(uint32_t sm_base, const float* _
                 uint32_t drow = sm_base + 4u * (uint32_t)(r0 * lstride + lane);
                 const uint32_t dstep = 4u * (uint32_t)(kLoaderWarps * lstride);
                 const int64_t sstep = (int64_t)kLoaderWarps * n0;
-#pragma unroll 2
-                for (int r = r0; r < re; r += kLoaderWarps, drow += dstep, rowp += sstep) {
-#pragma unroll
-                    for (int q = 0; q < NCH; ++q) {
-                        // byte address = row + 4 * offset as ONE IMAD.WIDE on the FMA pipe (the multiplier is a
-                        // run-time 4, so the compiler cannot turn it into the two-instruction LEA pair on the
-                        // ALU pipe, which this kernel saturates)
-                        const float* src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(rowp) +
-                                                                          (uint64_t)(uint32_t)c.off[q] * four);
-                        if (lane + 32 * q < span) cp_async4(drow + 128u * q, src);
-                    }
+                // whole 32-position chunks unconditionally, the partial chunk under one loop-invariant predicate (a compare
+                // per element is an ALU-pipe instruction: see relayout_rows)
+                const bool tail = lane < (span & 31);
+                switch (span >> 5) {
+                    case 0: fill_rows<0>(rowp, drow, sstep, dstep, r0, re, c.off, four, tail); break;
+                    case 1: fill_rows<1>(rowp, drow, sstep, dstep, r0, re, c.off, four, tail); break;
+                    case 2: fill_rows<2>(rowp, drow, sstep, dstep, r0, re, c.off, four, tail); break;
+                    case 3: fill_rows<3>(rowp, drow, sstep, dstep, r0, re, c.off, four, tail); break;
+                    case 4: fill_rows<4>(rowp, drow, sstep, dstep, r0, re, c.off, four, tail); break;
+                    case 5: fill_rows<5>(rowp, drow, sstep, dstep, r0, re, c.off, four, tail); break;
+                    case 6: fill_rows<6>(rowp, drow, sstep, dstep, r0, re, c.off, four, tail); break;
+                    default: fill_rows<7>(rowp, drow, sstep, dstep, r0, re, c.off, four, tail); break;
                 }
             };
             fill_run(0, rA, nA, fc[0]);
@@ -469,6 +488,9 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
 // source offsets of a lane's positions live in registers) -- instead of gathering it from global memory with
 // 4-byte cp.async (one copy per ~75 cycles and warp: the loader ring was the limit of this kernel for k <= 31).
 // Compute warps, selection networks and the coalesced store are those of median_fast_kernel.
+#ifndef HPSS_DENSE_MINK
+#define HPSS_DENSE_MINK 3     // smallest kernel size that takes the dense bulk-copy path (all of them since the loader lost its compares)
+#endif
 #ifndef HPSS_LAND
 #define HPSS_LAND 3
 #endif
@@ -488,6 +510,22 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// dense rows -> padded rows of one tile for the rows lw, lw + kLoaderWarps, ...: NF whole chunks of 32 positions
+// plus one partial chunk (`tail` = this lane takes part in it); span <= 32 * FillCache::kChunks
+template <int NF>
+__device__ __forceinline__ void relayout_rows(uint32_t src, uint32_t dst, uint32_t sstep, uint32_t dstep, int lw,
+                                              int rows_here, const uint32_t (&off4)[FillCache::kChunks], bool tail) {
+    for (int r = lw; r < rows_here; r += kLoaderWarps, src += sstep, dst += dstep) {
+        float v[NF + 1];
+#pragma unroll
+        for (int q = 0; q < NF; ++q) v[q] = lds_f32(src + off4[q]);
+        if (tail) v[NF] = lds_f32(src + off4[NF < FillCache::kChunks ? NF : 0]);
+#pragma unroll
+        for (int q = 0; q < NF; ++q) sts_f32(dst + 128u * q, v[q]);
+        if (tail) sts_f32(dst + 128u * NF, v[NF]);
+    }
 }
 
 template <int K>
@@ -560,12 +598,20 @@ median_dense_kernel(const float* __restrict__ S, float* __restrict__ out, int64_
             uint32_t dst = smem_u32(smem + (size_t)b * tile_floats) + 4u * (uint32_t)(lw * lstride + lane);
             const uint32_t sstep = 4u * (uint32_t)(kLoaderWarps * T), dstep = 4u * (uint32_t)(kLoaderWarps * lstride);
             // (four rows per iteration, all loads before the first store, was measured slower: 0.32 vs 0.24 ms at k = 31)
-            for (int r = lw; r < rows_here; r += kLoaderWarps, src += sstep, dst += dstep) {
-                float v[FillCache::kChunks];
-#pragma unroll
-                for (int q = 0; q < FillCache::kChunks; ++q) v[q] = (lane + 32 * q < span) ? lds_f32(src + off4[q]) : 0.f;
-#pragma unroll
-                for (int q = 0; q < FillCache::kChunks; ++q) if (lane + 32 * q < span) sts_f32(dst + 128u * q, v[q]);
+            // The number of whole 32-position chunks of a row is a compile-time constant of the copy loop (dispatched
+            // once per tile) and the predicate of the partial chunk is loop invariant: no compare per element (ISETP
+            // runs on the ALU pipe, which the selection networks saturate; the predicated version spent 9 % of the
+            // kernel's ALU-pipe time on them).
+            const bool tail = lane < (span & 31);
+            switch (span >> 5) {
+                case 0: relayout_rows<0>(src, dst, sstep, dstep, lw, rows_here, off4, tail); break;
+                case 1: relayout_rows<1>(src, dst, sstep, dstep, lw, rows_here, off4, tail); break;
+                case 2: relayout_rows<2>(src, dst, sstep, dstep, lw, rows_here, off4, tail); break;
+                case 3: relayout_rows<3>(src, dst, sstep, dstep, lw, rows_here, off4, tail); break;
+                case 4: relayout_rows<4>(src, dst, sstep, dstep, lw, rows_here, off4, tail); break;
+                case 5: relayout_rows<5>(src, dst, sstep, dstep, lw, rows_here, off4, tail); break;
+                case 6: relayout_rows<6>(src, dst, sstep, dstep, lw, rows_here, off4, tail); break;
+                default: relayout_rows<7>(src, dst, sstep, dstep, lw, rows_here, off4, tail); break;
             }
             mbar_arrive(full0 + 8u * b);
             __syncwarp();
@@ -702,7 +748,7 @@ int launch_fast(hpss_ctx* ctx, const hpss_batch* b, const float* S, float* out, 
         // equal clips whose whole line fits one tile, 16-byte aligned input: one bulk copy per tile (median_dense_kernel)
         // (measured on the 4096 x 1 s batch: k = 31 0.248 -> 0.242 ms, k = 41 0.351 -> 0.339 ms, but k = 21 0.224 -> 0.231 ms
         // and k = 11 0.201 -> 0.212 ms: below ~25 taps the tile period is too short for the two-stage pipeline)
-        if (K >= 25 && uniform_T > 0 && n_ptiles == 1 && span <= 32 * FillCache::kChunks && !knobs().no_dense_median &&
+        if (K >= HPSS_DENSE_MINK && uniform_T > 0 && n_ptiles == 1 && span < 32 * FillCache::kChunks && !knobs().no_dense_median &&
             (reinterpret_cast<uintptr_t>(S) & 15) == 0) {
             const size_t land_bytes = (((size_t)32 * uniform_T + 31) & ~(size_t)31) * sizeof(float);
             const size_t fixed = kLand * land_bytes + 128 + 16 * (size_t)kLand + 256;

@@ -4,12 +4,15 @@ Bars (BASELINE.json north_star): medians and frame indexing bit-exact; soft-mask
 bit-exact given identical (S, harm, perc); STFT / features within 1e-4 relative L2 (max-abs
 reported in the assertion message).
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import librosa_restated as lr
 from oracle import preprocessing_oracle as po
+from sm_hpss_mtl_b200._lib import check
 from sm_hpss_mtl_b200 import engine, synth
 
 pytestmark = pytest.mark.gpu
@@ -62,6 +65,34 @@ def test_median_bit_exact(ctx, rows, Ts, k):
             assert np.array_equal(h.cpu().numpy(), lr.median_filter_scipy(mats[c], k, axis=1))
         if lr.scipy_median_well_defined(rows, k):
             assert np.array_equal(p.cpu().numpy(), lr.median_filter_scipy(mats[c], k, axis=0))
+
+
+@pytest.mark.parametrize("k", [25, 31, 41, 63])
+@pytest.mark.parametrize("n_clips,rows,T", [(1, 201, 98), (3, 201, 98), (5, 7, 33), (2, 64, 5), (4, 33, 150), (1, 1, 2), (9, 11, 27)])
+def test_median_time_dense_tiles(ctx, k, n_clips, rows, T):
+    """Batches of equal clips take the bulk-copy tile path for k >= 25 (median_dense_kernel): whole tiles and a
+    partial last tile (lines not a multiple of 32, byte count not a multiple of 16), lines shorter than the halo
+    (several reflections), canary regions around the output, and an input that is NOT 16-byte aligned (falls back
+    to the cp.async ring): bit-exact against the oracle each time."""
+    rng = np.random.default_rng(k * 131 + rows * 7 + T)
+    mats = [np.abs(rng.standard_normal((rows, T))).astype(np.float32) for _ in range(n_clips)]
+    mats = [np.where(rng.random(m.shape) < 0.3, np.round(m * 4) / 4, m).astype(np.float32) for m in mats]
+    batch = engine.Batch(ctx, clip_frames=[T] * n_clips)
+    flat = flat_batch(mats)
+    for shift in (0, 1):                                   # 1: the input starts 4 bytes after a 16-byte boundary
+        buf = torch.zeros(flat.size + 8, dtype=torch.float32, device="cuda")
+        S = buf[shift:shift + flat.size]
+        S.copy_(torch.from_numpy(flat))
+        pad = 512
+        big = torch.full((flat.size + 2 * pad,), -7.0, dtype=torch.float32, device="cuda")
+        out = big[pad:pad + flat.size]
+        check(batch.lib.hpss_median_time(batch.ctx.handle, batch.handle, C.c_void_p(S.data_ptr()), rows, k,
+                                         C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        assert bool((big[:pad] == -7.0).all()) and bool((big[pad + flat.size:] == -7.0).all())
+        for c, m in enumerate(mats):
+            got = batch.clip(out, rows, c).cpu().numpy()
+            assert np.array_equal(got, lr.median_filter_1d(m, k, axis=1)), (shift, c)
 
 
 def test_median_all_fast_kernel_sizes(ctx):
