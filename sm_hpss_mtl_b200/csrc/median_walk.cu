@@ -27,12 +27,29 @@ namespace {
 #endif
 constexpr int kWalkWarps = 4;
 
-// p + i * pitch_bytes as ONE IMAD.WIDE.U32 (FMA pipe): the ALU pipe belongs to the FMNMX stream
-__device__ __forceinline__ const float* row_ptr(const float* p, uint32_t i, uint32_t pitch_bytes) {
-    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p) + (uint64_t)i * pitch_bytes);
+// Addressing without the ALU pipe (it belongs to the FMNMX stream): an element of the lane's clip is
+// clip_base[i0 + row * T] with a 32-bit index, i.e. one IMAD (index) and one IMAD.WIDE.U32 (address), both on the
+// FMA pipe.  The index is formed in PTX: left to the compiler the row loop becomes 64-bit pointer increments
+// (IADD3 + IMAD.X per row) or, with mad.wide and a 64-bit addend, a split product + IADD3 -- ALU pipe either way.
+// The launcher checks rows * max_frames < 2^32.
+__device__ __forceinline__ uint32_t row_idx(uint32_t i0, uint32_t row, uint32_t T) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(T), "r"(row), "r"(i0));
+    return r;
 }
-__device__ __forceinline__ float* row_ptr(float* p, uint32_t i, uint32_t pitch_bytes) {
-    return reinterpret_cast<float*>(reinterpret_cast<char*>(p) + (uint64_t)i * pitch_bytes);
+// base + 4 * idx, also in PTX: the compiler would fold the clip base into the index and rebuild a 64-bit address
+// from the kernel argument with IADD3 / LEA / LEA.HI.X
+__device__ __forceinline__ float load_elem(const float* base, uint32_t idx, uint64_t four) {
+    uint64_t a;
+    float v;
+    asm("{\n\t.reg .u64 t;\n\tcvt.u64.u32 t, %1;\n\tmad.lo.u64 %0, t, %2, %3;\n\t}" : "=l"(a) : "r"(idx), "l"(four), "l"(base));
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(a));
+    return v;
+}
+__device__ __forceinline__ void store_elem(float* base, uint32_t idx, uint64_t four, float v) {
+    uint64_t a;
+    asm("{\n\t.reg .u64 t;\n\tcvt.u64.u32 t, %1;\n\tmad.lo.u64 %0, t, %2, %3;\n\t}" : "=l"(a) : "r"(idx), "l"(four), "l"(base));
+    asm volatile("st.global.f32 [%0], %1;" ::"l"(a), "f"(v) : "memory");
 }
 
 template <int K>
@@ -47,24 +64,19 @@ median_freq_walk_kernel(const float* __restrict__ S, float* __restrict__ perc, c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t g0 = ((int64_t)blockIdx.x * kWalkWarps + warp) * 32;
     if (g0 >= total_frames) return;
-    const int64_t gf = g0 + lane;
-    const bool valid = gf < total_frames;
-    int64_t T = 1, fo = 0;
-    if (valid) {
-        const int clip = find_clip_hint(frame_off, block_clip, gf);
-        fo = __ldg(frame_off + clip);
-        T = __ldg(frame_off + clip + 1) - fo;
-    }
-    const int64_t in_base = (int64_t)rows * fo + (gf - fo);
-    const float* col = S + in_base;
-    const int Ti = (int)T;                     // row pitch of this lane's clip
-    const uint32_t T4 = 4u * (uint32_t)Ti;     // ... in bytes: one IMAD.WIDE.U32 per address
+    // lanes past the last frame of the batch work on the last frame as well (same loads, same values stored to
+    // the same addresses): no per-access predicate, whose compares would sit on the ALU pipe
+    const int64_t gf = min(g0 + lane, total_frames - 1);
+    const int clip = find_clip_hint(frame_off, block_clip, gf);
+    const int64_t fo = __ldg(frame_off + clip);
+    const int64_t T64 = __ldg(frame_off + clip + 1) - fo;
+    const uint32_t T = (uint32_t)T64;                                     // row pitch of this lane's clip
+    const uint32_t i0 = (uint32_t)(gf - fo);                              // the lane's frame inside its clip
+    const uint64_t four = 4u + ((uint64_t)T64 >> 31);                                 // = 4, in a per-lane register: load_elem()
+    const float* __restrict__ Sc = S + (int64_t)rows * fo;
+    float* __restrict__ Pc = perc + (int64_t)rows * fo;
     // S[f] of this lane's frame, f reflected into [0, rows) (warp-uniform index)
-    auto ld = [&](int f) -> float {
-        const int fr = reflect_idx(f, rows);
-        return valid ? __ldg(row_ptr(col, (uint32_t)fr, T4)) : 0.f;
-    };
-    float* pcol = perc + in_base;
+    auto ld = [&](int f) -> float { return load_elem(Sc, row_idx(i0, (uint32_t)reflect_idx(f, rows), T), four); };
 
     // ---- prologue: x[i] = S[-HALO + i], i = 0 .. 2G + K - 2 of step 0
     // raw values carried between steps: lx = x[0..G-2], mid = x[G..2G-2], c1 = x[2G-1..3G-2], hi = x[3G-1..4G-3]
@@ -104,23 +116,21 @@ median_freq_walk_kernel(const float* __restrict__ S, float* __restrict__ perc, c
         // the 2G new input rows of the next step: in flight during the stores
         float nn[2 * G];
         if (interior) {
-            const float* np = row_ptr(col, (uint32_t)(base + 4 * G - 1), T4);
+            const uint32_t in = row_idx(i0, (uint32_t)(base + 4 * G - 1), T);
 #pragma unroll
-            for (int i = 0; i < 2 * G; ++i) nn[i] = valid ? __ldg(row_ptr(np, i, T4)) : 0.f;
+            for (int i = 0; i < 2 * G; ++i) nn[i] = load_elem(Sc, row_idx(in, i, T), four);
         } else if (s + 1 < nsteps) {
 #pragma unroll
             for (int i = 0; i < 2 * G; ++i) nn[i] = ld(base + 4 * G - 1 + i);
         }
-        if (valid) {
-            float* dst = row_ptr(pcol, (uint32_t)base, T4);
-            if (interior) {
+        const uint32_t io = row_idx(i0, (uint32_t)base, T);
+        if (interior) {
 #pragma unroll
-                for (int j = 0; j < 2 * G; ++j) *row_ptr(dst, j, T4) = o[j];
-            } else {
+            for (int j = 0; j < 2 * G; ++j) store_elem(Pc, row_idx(io, j, T), four, o[j]);
+        } else {
 #pragma unroll
-                for (int j = 0; j < 2 * G; ++j)
-                    if (base + j < rows) *row_ptr(dst, j, T4) = o[j];
-            }
+            for (int j = 0; j < 2 * G; ++j)
+                if (base + j < rows) store_elem(Pc, row_idx(io, j, T), four, o[j]);
         }
         // carry the raw values the next step reads again: x'[i] = x[i + 2G]
 #pragma unroll
@@ -150,23 +160,16 @@ median_freq_walk_group_kernel(const float* __restrict__ S, float* __restrict__ p
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t g0 = ((int64_t)blockIdx.x * kWalkWarps + warp) * 32;
     if (g0 >= total_frames) return;
-    const int64_t gf = g0 + lane;
-    const bool valid = gf < total_frames;
-    int64_t fo = 0;
-    int Ti = 1;
-    if (valid) {
-        const int clip = find_clip_hint(frame_off, block_clip, gf);
-        fo = __ldg(frame_off + clip);
-        Ti = (int)(__ldg(frame_off + clip + 1) - fo);
-    }
-    const int64_t in_base = (int64_t)rows * fo + (gf - fo);
-    const float* col = S + in_base;
-    float* pcol = perc + in_base;
-    const uint32_t T4 = 4u * (uint32_t)Ti;
-    auto ld = [&](int f) -> float {
-        const int fr = reflect_idx(f, rows);
-        return valid ? __ldg(row_ptr(col, (uint32_t)fr, T4)) : 0.f;
-    };
+    const int64_t gf = min(g0 + lane, total_frames - 1);      // see median_freq_walk_kernel
+    const int clip = find_clip_hint(frame_off, block_clip, gf);
+    const int64_t fo = __ldg(frame_off + clip);
+    const int64_t T64 = __ldg(frame_off + clip + 1) - fo;
+    const uint32_t T = (uint32_t)T64;
+    const uint32_t i0 = (uint32_t)(gf - fo);
+    const uint64_t four = 4u + ((uint64_t)T64 >> 31);
+    const float* __restrict__ Sc = S + (int64_t)rows * fo;
+    float* __restrict__ Pc = perc + (int64_t)rows * fo;
+    auto ld = [&](int f) -> float { return load_elem(Sc, row_idx(i0, (uint32_t)reflect_idx(f, rows), T), four); };
     float x[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = ld(-HALO + i);
@@ -178,21 +181,19 @@ median_freq_walk_group_kernel(const float* __restrict__ S, float* __restrict__ p
         const bool interior = fnew + G - 1 < rows;          // warp-uniform: no reflection in the next loads
         float nn[G];
         if (interior) {
-            const float* np = row_ptr(col, (uint32_t)fnew, T4);
+            const uint32_t in = row_idx(i0, (uint32_t)fnew, T);
 #pragma unroll
-            for (int j = 0; j < G; ++j) nn[j] = valid ? __ldg(row_ptr(np, j, T4)) : 0.f;
+            for (int j = 0; j < G; ++j) nn[j] = load_elem(Sc, row_idx(in, j, T), four);
         } else if (g + 1 < ngroups) {
 #pragma unroll
             for (int j = 0; j < G; ++j) nn[j] = ld(fnew + j);
         }
         float o[G];
         MedianGroup<K>::run(x, o);
-        if (valid) {
-            float* dst = row_ptr(pcol, (uint32_t)base, T4);
+        const uint32_t io = row_idx(i0, (uint32_t)base, T);
 #pragma unroll
-            for (int j = 0; j < G; ++j)
-                if (base + j < rows) *row_ptr(dst, j, T4) = o[j];
-        }
+        for (int j = 0; j < G; ++j)
+            if (base + j < rows) store_elem(Pc, row_idx(io, j, T), four, o[j]);
 #pragma unroll
         for (int i = 0; i < K - 1; ++i) x[i] = x[i + G];
 #pragma unroll
@@ -208,6 +209,7 @@ int launch_median_freq_walk(hpss_ctx* ctx, const hpss_batch* b, const float* S, 
     (void)ctx;
     *handled = false;
     const int64_t total = b->frame_off[b->n_clips];
+    if ((int64_t)rows * b->max_frames > 0xffffffffLL) return HPSS_OK;      // 32-bit indices inside a clip (row_idx)
 #define HPSS_WALK_ANY_K(KK)                                                                                         \
     if (k == KK) {                                                                                                  \
         *handled = true;                                                                                            \
