@@ -278,6 +278,36 @@ __device__ __forceinline__ int find_clip_hint(const int64_t* __restrict__ off, c
     return c;
 }
 
+// ---- addressing without the ALU pipe ------------------------------------------------------------------------------
+// The median kernels saturate the ALU pipe with FMNMX (half rate); every IADD3 / VIADD / LEA / ISETP of the address
+// arithmetic around them takes a slot of that pipe.  These helpers keep the address arithmetic on the FMA pipe:
+//   fma_pipe_mad    a * b + c in 32 bits as one IMAD (PTX, so that the compiler cannot strength-reduce a row loop into
+//                   pointer increments = IADD3 + IMAD.X per row)
+//   fma_pipe_load / fma_pipe_store   base[idx] with a 32-bit element index: IMAD.WIDE.U32 + IMAD.  The element size is
+//                   passed as a 64-bit value `four` the compiler cannot see through (callers derive it from loaded data:
+//                   4 + (x >> 40) with x < 2^40): with an immediate 4 ptxas emits LEA + LEA.HI.X, with mad.wide.u32 and a
+//                   64-bit addend it splits the product from an IADD3 + IMAD.X add -- ALU pipe both times (sm_100a,
+//                   CUDA 12.9; SASS checked with cuobjdump).
+__device__ __forceinline__ uint32_t fma_pipe_mad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma_pipe_addr(const void* base, uint32_t idx, uint64_t elem_bytes) {
+    uint64_t a;
+    asm("{\n\t.reg .u64 t;\n\tcvt.u64.u32 t, %1;\n\tmad.lo.u64 %0, t, %2, %3;\n\t}"
+        : "=l"(a) : "r"(idx), "l"(elem_bytes), "l"(base));
+    return a;
+}
+__device__ __forceinline__ float fma_pipe_load(const float* base, uint32_t idx, uint64_t four) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(fma_pipe_addr(base, idx, four)));
+    return v;
+}
+__device__ __forceinline__ void fma_pipe_store(float* base, uint32_t idx, uint64_t four, float v) {
+    asm volatile("st.global.f32 [%0], %1;" ::"l"(fma_pipe_addr(base, idx, four)), "f"(v) : "memory");
+}
+
 // order-preserving float <-> uint mapping for atomicMax on floats of either sign
 __device__ __forceinline__ uint32_t float_to_ordered(float x) {
     const uint32_t u = __float_as_uint(x);

@@ -424,15 +424,19 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
         LineInfo li;
         li.base = 0; li.n = 0; li.estride = 1;
         int64_t li_lb = -1;
-        for (int64_t n = 0; n < my_items; ++n) {
-            const int b = (int)(n % NB);
-            const uint32_t use = (uint32_t)(n / NB);
-            const int64_t item = blockIdx.x + n * gridDim.x;
+        // ring slot and parity are running counters: a division / modulo per tile and warp is ~30 ALU-pipe instructions
+        int b = 0;
+        uint32_t bphase = 1;                               // parity of the buffer's previous release
+        bool bfirst = true;
+        int64_t item = blockIdx.x;
+        for (int64_t n = 0; n < my_items; ++n, item += gridDim.x) {
             int64_t lb;
             int p0;
             if (tile_list != nullptr) {                    // ragged batch: explicit list of the tiles that exist
                 const int2 tl = __ldg(tile_list + item);
                 lb = tl.x; p0 = tl.y;
+            } else if (n_ptiles == 1) {
+                lb = item; p0 = 0;
             } else {
                 lb = item / n_ptiles;
                 p0 = (int)(item - lb * n_ptiles) * TT;
@@ -441,25 +445,28 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
                 li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane, uniform_T);
                 li_lb = lb;
             }
-            if (use > 0) mbar_wait(empty0 + 8u * b, (use - 1) & 1u);
+            if (!bfirst) mbar_wait(empty0 + 8u * b, bphase);
             tile_fill_async<TIME_AXIS>(smem_u32(smem + (size_t)b * tile_floats), S, li, lane, lw, p0, HALO, span, lstride, fc);
             cp_async_arrive(full0 + 8u * b);
+            if (++b == NB) { b = 0; bphase ^= 1u; bfirst = false; }
         }
     } else {
         // ===== compute warps =====
         LineInfo li;
         li.base = 0; li.n = 0; li.estride = 1;
         int64_t li_lb = -1;
-        for (int64_t n = warp; n < my_items; n += kComputeWarps) {
-            const int b = (int)(n % NB);
-            const uint32_t use = (uint32_t)(n / NB);
+        int b = warp % NB;
+        uint32_t phase = (uint32_t)(warp / NB) & 1u;
+        int64_t item = blockIdx.x + (int64_t)warp * gridDim.x;
+        for (int64_t n = warp; n < my_items; n += kComputeWarps, item += (int64_t)kComputeWarps * gridDim.x) {
             float* sm = smem + (size_t)b * tile_floats;
-            const int64_t item = blockIdx.x + n * gridDim.x;
             int64_t lb;
             int p0;
             if (tile_list != nullptr) {                    // ragged batch: explicit list of the tiles that exist
                 const int2 tl = __ldg(tile_list + item);
                 lb = tl.x; p0 = tl.y;
+            } else if (n_ptiles == 1) {
+                lb = item; p0 = 0;
             } else {
                 lb = item / n_ptiles;
                 p0 = (int)(item - lb * n_ptiles) * TT;
@@ -468,7 +475,7 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
                 li = lane_line<TIME_AXIS>(frame_off, block_clip, rows, n_lines, lb * 32 + lane, uniform_T);
                 li_lb = lb;
             }
-            mbar_wait(full0 + 8u * b, use & 1u);
+            mbar_wait(full0 + 8u * b, phase);
             median_compute_tile<K, TIME_AXIS>(sm, out, li, lane, p0, TT, lstride);
             __syncwarp();
             if (TIME_AXIS) {
@@ -476,6 +483,8 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
                 __syncwarp();
             }
             if (lane == 0) mbar_arrive(empty0 + 8u * b);
+            b += kComputeWarps;
+            while (b >= NB) { b -= NB; phase ^= 1u; }
         }
     }
 }
@@ -493,6 +502,9 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
 #endif
 #ifndef HPSS_LAND
 #define HPSS_LAND 3
+#endif
+#ifndef HPSS_RELAYOUT_FULL
+#define HPSS_RELAYOUT_FULL 1
 #endif
 constexpr int kLand = HPSS_LAND;  // landing buffers
 
@@ -515,17 +527,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // dense rows -> padded rows of one tile for the rows lw, lw + kLoaderWarps, ...: NF whole chunks of 32 positions
 // plus one partial chunk (`tail` = this lane takes part in it); span <= 32 * FillCache::kChunks
 template <int NF>
+__device__ __forceinline__ void relayout_row(uint32_t src, uint32_t dst, const uint32_t (&off4)[FillCache::kChunks],
+                                             bool tail) {
+    float v[NF + 1];
+#pragma unroll
+    for (int q = 0; q < NF; ++q) v[q] = lds_f32(src + off4[q]);
+    if (tail) v[NF] = lds_f32(src + off4[NF < FillCache::kChunks ? NF : 0]);
+#pragma unroll
+    for (int q = 0; q < NF; ++q) sts_f32(dst + 128u * q, v[q]);
+    if (tail) sts_f32(dst + 128u * NF, v[NF]);
+}
+template <int NF>
 __device__ __forceinline__ void relayout_rows(uint32_t src, uint32_t dst, uint32_t sstep, uint32_t dstep, int lw,
                                               int rows_here, const uint32_t (&off4)[FillCache::kChunks], bool tail) {
-    for (int r = lw; r < rows_here; r += kLoaderWarps, src += sstep, dst += dstep) {
-        float v[NF + 1];
+    if (HPSS_RELAYOUT_FULL && rows_here == 32) {              // every tile but the last: no loop counter, no compare (ALU pipe)
 #pragma unroll
-        for (int q = 0; q < NF; ++q) v[q] = lds_f32(src + off4[q]);
-        if (tail) v[NF] = lds_f32(src + off4[NF < FillCache::kChunks ? NF : 0]);
-#pragma unroll
-        for (int q = 0; q < NF; ++q) sts_f32(dst + 128u * q, v[q]);
-        if (tail) sts_f32(dst + 128u * NF, v[NF]);
+        for (int i = 0; i < 32 / kLoaderWarps; ++i) relayout_row<NF>(src + i * sstep, dst + i * dstep, off4, tail);
+        return;
     }
+    for (int r = lw; r < rows_here; r += kLoaderWarps, src += sstep, dst += dstep) relayout_row<NF>(src, dst, off4, tail);
 }
 
 template <int K>
@@ -555,7 +575,9 @@ median_dense_kernel(const float* __restrict__ S, float* __restrict__ out, int64_
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
-    const int64_t my_items = (n_items > blockIdx.x) ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // items of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...  Ring slots and phases are running counters (a
+    // division / modulo per tile and warp is ~30 ALU-pipe instructions); the launcher keeps the count below 2^31.
+    const int my_items = (n_items > blockIdx.x) ? (int)((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
     auto tile_rows = [&](int64_t item) { return (int)min((int64_t)32, n_lines - item * 32); };
 
     if (warp >= kComputeWarps) {
@@ -565,37 +587,41 @@ median_dense_kernel(const float* __restrict__ S, float* __restrict__ out, int64_
         uint32_t off4[FillCache::kChunks];
 #pragma unroll
         for (int q = 0; q < FillCache::kChunks; ++q) off4[q] = 4u * (uint32_t)reflect_idx(lane + 32 * q - HALO, T);
-        auto issue = [&](int64_t n) {                              // elected thread: bulk copy of item n
-            const int slot = (int)(n % kLand);
-            const uint32_t use = (uint32_t)(n / kLand);
-            if (use > 0) mbar_wait(lempty0 + 8u * slot, (use - 1) & 1u);
-            const int64_t item = blockIdx.x + n * gridDim.x;
-            const uint32_t bytes = ((uint32_t)tile_rows(item) * (uint32_t)T * 4u) & ~15u;
-            mbar_expect_tx(lfull0 + 8u * slot, bytes);
-            if (bytes) bulk_load(smem_u32(land0 + (size_t)slot * land_floats), S + item * 32 * (int64_t)T, bytes, lfull0 + 8u * slot);
+        int islot = 0;                                             // landing slot / its use parity of the next issue
+        uint32_t iphase = 1;                                       // (parity of use - 1: first round never waits)
+        int64_t iitem = blockIdx.x;
+        bool ifirst = true;
+        auto issue = [&]() {                                       // elected thread: bulk copy of the next item
+            if (!ifirst) mbar_wait(lempty0 + 8u * islot, iphase);
+            const uint32_t bytes = ((uint32_t)tile_rows(iitem) * (uint32_t)T * 4u) & ~15u;
+            mbar_expect_tx(lfull0 + 8u * islot, bytes);
+            if (bytes) bulk_load(smem_u32(land0 + (size_t)islot * land_floats), S + iitem * 32 * (int64_t)T, bytes, lfull0 + 8u * islot);
+            iitem += gridDim.x;
+            if (++islot == kLand) { islot = 0; iphase ^= 1u; ifirst = false; }
         };
         const bool elected = lw == 0 && lane == 0;
         if (elected)
-            for (int64_t n = 0; n < min((int64_t)(kLand - 1), my_items); ++n) issue(n);
-        for (int64_t n = 0; n < my_items; ++n) {
-            if (elected && n + kLand - 1 < my_items) issue(n + kLand - 1);
-            const int slot = (int)(n % kLand);
-            const int b = (int)(n % NB);
-            const uint32_t use = (uint32_t)(n / NB);
-            const int64_t item = blockIdx.x + n * gridDim.x;
+            for (int n = 0; n < min(kLand - 1, my_items); ++n) issue();
+        int slot = 0, b = 0;
+        uint32_t lphase = 0, bphase = 1;                           // parity to wait for: landing full / tile empty
+        bool bfirst = true;
+        int64_t item = blockIdx.x;
+        const uint32_t land_b = smem_u32(land0), tile_b = smem_u32(smem);
+        for (int n = 0; n < my_items; ++n, item += gridDim.x) {
+            if (elected && n + kLand - 1 < my_items) issue();
             const int rows_here = tile_rows(item);
-            const float* land = land0 + (size_t)slot * land_floats;
-            mbar_wait(lfull0 + 8u * slot, (uint32_t)(n / kLand) & 1u);
-            {   // the (at most three) floats behind the last 16-byte unit of a partial last tile
+            const uint32_t land = land_b + 4u * (uint32_t)(slot * land_floats);
+            mbar_wait(lfull0 + 8u * slot, lphase);
+            if (rows_here != 32) {   // the (at most three) floats behind the last 16-byte unit of a partial last tile
                 const int got = (int)((((uint32_t)rows_here * (uint32_t)T * 4u) & ~15u) / 4u), want = rows_here * T;
                 if (lw == 0 && got + lane < want)
-                    const_cast<float*>(land)[got + lane] = __ldg(S + item * 32 * (int64_t)T + got + lane);
+                    sts_f32(land + 4u * (uint32_t)(got + lane), __ldg(S + item * 32 * (int64_t)T + got + lane));
                 if (got != want) asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kLoaderWarps) : "memory");
             }
-            if (use > 0) mbar_wait(empty0 + 8u * b, (use - 1) & 1u);
+            if (!bfirst) mbar_wait(empty0 + 8u * b, bphase);
             // 32-bit shared-memory addresses: one add per access (generic pointers cost four ALU instructions each)
-            uint32_t src = smem_u32(land) + 4u * (uint32_t)(lw * T);
-            uint32_t dst = smem_u32(smem + (size_t)b * tile_floats) + 4u * (uint32_t)(lw * lstride + lane);
+            const uint32_t src = land + 4u * (uint32_t)(lw * T);
+            const uint32_t dst = tile_b + 4u * (uint32_t)(b * tile_floats + lw * lstride + lane);
             const uint32_t sstep = 4u * (uint32_t)(kLoaderWarps * T), dstep = 4u * (uint32_t)(kLoaderWarps * lstride);
             // (four rows per iteration, all loads before the first store, was measured slower: 0.32 vs 0.24 ms at k = 31)
             // The number of whole 32-position chunks of a row is a compile-time constant of the copy loop (dispatched
@@ -616,24 +642,30 @@ median_dense_kernel(const float* __restrict__ S, float* __restrict__ out, int64_
             mbar_arrive(full0 + 8u * b);
             __syncwarp();
             if (lane == 0) mbar_arrive(lempty0 + 8u * slot);
+            if (++slot == kLand) { slot = 0; lphase ^= 1u; }
+            if (++b == NB) { b = 0; bphase ^= 1u; bfirst = false; }
         }
     } else {
         // ===== compute warps =====
-        for (int64_t n = warp; n < my_items; n += kComputeWarps) {
-            const int b = (int)(n % NB);
-            const uint32_t use = (uint32_t)(n / NB);
+        int b = warp;                                              // NB > kComputeWarps: at most one wrap per item
+        uint32_t phase = 0;
+        int64_t item = blockIdx.x + (int64_t)warp * gridDim.x;
+        for (int n = warp; n < my_items; n += kComputeWarps, item += (int64_t)kComputeWarps * gridDim.x) {
             float* sm = smem + (size_t)b * tile_floats;
-            const int64_t item = blockIdx.x + n * gridDim.x;
             LineInfo li;
             li.estride = 1;
             li.n = (item * 32 + lane < n_lines) ? T : 0;
             li.base = (item * 32 + lane) * (int64_t)T;
-            mbar_wait(full0 + 8u * b, use & 1u);
+            mbar_wait(full0 + 8u * b, phase);
             median_compute_tile<K, true>(sm, out, li, lane, 0, TT, lstride);
             __syncwarp();
+            // (a store with every address formed on the FMA pipe -- fma_pipe_store, rows unrolled 4 / 8 / 32 times --
+            // was measured slower than this one at every kernel size: 0.224 - 0.241 vs 0.220 ms at k = 31)
             tile_store<true>(sm, out, li, lane, 0, TT, lstride);
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8u * b);
+            b += kComputeWarps;
+            if (b >= NB) { b -= NB; phase ^= 1u; }
         }
     }
 }
@@ -760,6 +792,7 @@ int launch_fast(hpss_ctx* ctx, const hpss_batch* b, const float* S, float* out, 
                 HPSS_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
                 int64_t gd = (n_lb + kComputeWarps - 1) / kComputeWarps;
                 if (gd > ctx->sm_count) gd = ctx->sm_count;
+                if (n_lb / gd >= 0x7fffffff) { set_error("median: batch too large"); return HPSS_ERR_UNSUPPORTED; }
                 kd<<<(unsigned)gd, kRingThreads, smem_d, st>>>(S, out, n_lines, uniform_T, TT, n_lb, NBd);
                 HPSS_LAUNCHED("median_dense_kernel");
                 return HPSS_OK;

@@ -27,29 +27,14 @@ namespace {
 #endif
 constexpr int kWalkWarps = 4;
 
-// Addressing without the ALU pipe (it belongs to the FMNMX stream): an element of the lane's clip is
-// clip_base[i0 + row * T] with a 32-bit index, i.e. one IMAD (index) and one IMAD.WIDE.U32 (address), both on the
-// FMA pipe.  The index is formed in PTX: left to the compiler the row loop becomes 64-bit pointer increments
-// (IADD3 + IMAD.X per row) or, with mad.wide and a 64-bit addend, a split product + IADD3 -- ALU pipe either way.
-// The launcher checks rows * max_frames < 2^32.
-__device__ __forceinline__ uint32_t row_idx(uint32_t i0, uint32_t row, uint32_t T) {
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(T), "r"(row), "r"(i0));
-    return r;
-}
-// base + 4 * idx, also in PTX: the compiler would fold the clip base into the index and rebuild a 64-bit address
-// from the kernel argument with IADD3 / LEA / LEA.HI.X
+// Addresses come from the FMA pipe (fma_pipe_* in common.cuh): an element of the lane's clip is clip_base[i0 + row * T]
+// with a 32-bit index.  The launcher checks rows * max_frames < 2^32.
+__device__ __forceinline__ uint32_t row_idx(uint32_t i0, uint32_t row, uint32_t T) { return fma_pipe_mad(T, row, i0); }
 __device__ __forceinline__ float load_elem(const float* base, uint32_t idx, uint64_t four) {
-    uint64_t a;
-    float v;
-    asm("{\n\t.reg .u64 t;\n\tcvt.u64.u32 t, %1;\n\tmad.lo.u64 %0, t, %2, %3;\n\t}" : "=l"(a) : "r"(idx), "l"(four), "l"(base));
-    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(a));
-    return v;
+    return fma_pipe_load(base, idx, four);
 }
 __device__ __forceinline__ void store_elem(float* base, uint32_t idx, uint64_t four, float v) {
-    uint64_t a;
-    asm("{\n\t.reg .u64 t;\n\tcvt.u64.u32 t, %1;\n\tmad.lo.u64 %0, t, %2, %3;\n\t}" : "=l"(a) : "r"(idx), "l"(four), "l"(base));
-    asm volatile("st.global.f32 [%0], %1;" ::"l"(a), "f"(v) : "memory");
+    fma_pipe_store(base, idx, four, v);
 }
 
 template <int K>
