@@ -126,7 +126,7 @@ struct hpss_batch {
     std::map<std::pair<int, int>, std::pair<std::vector<int64_t>, int64_t*>> patch_offs;
     // K2h tile lists of ragged batches, one per (rows, tile length): the (line block, first position) pairs that
     // actually exist (a grid over the longest clip would be mostly empty for MUSAN-shaped length distributions)
-    std::map<std::pair<int, int>, std::pair<int2*, int64_t>> time_tiles;
+    std::map<std::pair<int, int>, std::pair<int64_t*, int64_t>> time_tiles;   // (rows, TT) -> tile prefix per line block, tiles
 };
 
 namespace hpss { struct PrepPlan; }

@@ -385,11 +385,38 @@ __device__ __forceinline__ void median_compute_tile(float* __restrict__ sm, floa
     }
 }
 
+// Tile number -> (line block, first position) in a ragged batch.  tile_first[lb] = tiles of the line blocks before lb
+// (n_lb + 1 entries).  A warp's tile numbers only grow, so after one binary search it walks the table forwards: one
+// global load per line block (~250 tiles of a MUSAN clip), none per tile.  (A list entry per tile cost a dependent
+// global load at the top of every loader iteration -- 24 % of the loader warps' time in ncu even when it was issued an
+// iteration ahead, because the compiler renames the prefetched register with a move that waits for the load.)
+struct TileWalk {
+    int64_t lb = -1, first = 0, last = 0;                  // tiles [first, last) belong to line block lb
+    __device__ __forceinline__ void locate(const int64_t* __restrict__ tile_first, int64_t n_lb, int64_t item) {
+        if (item < last) return;
+        if (lb < 0) {                                      // largest lb with tile_first[lb] <= item
+            int64_t lo = 0, hi = n_lb - 1;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi + 1) >> 1;
+                if (__ldg(tile_first + mid) <= item) lo = mid; else hi = mid - 1;
+            }
+            lb = lo;
+            first = __ldg(tile_first + lo);
+            last = __ldg(tile_first + lo + 1);
+        }
+        while (item >= last) {                             // (empty line blocks: clips without frames)
+            ++lb;
+            first = last;
+            last = __ldg(tile_first + lb + 1);
+        }
+    }
+};
+
 template <int K, bool TIME_AXIS>
 __global__ void __launch_bounds__(kRingThreads, 1)
 median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const int64_t* __restrict__ frame_off,
                    const int32_t* __restrict__ block_clip, int rows, int64_t n_lines, int TT, int n_ptiles,
-                   int64_t n_items, int NB, int uniform_T, const int2* __restrict__ tile_list) {
+                   int64_t n_items, int NB, int uniform_T, const int64_t* __restrict__ tile_first) {
     constexpr int G = MedianGroup<K>::G;
     constexpr int HALO = K / 2;
     // stateful double steps where K has them (time axis; the frequency axis has its own walk kernel).  MIXED:
@@ -415,7 +442,14 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
     }
     __syncthreads();
 
-    const int64_t my_items = (n_items > blockIdx.x) ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // A CTA owns a CONTIGUOUS range of the tile sequence (tiles of one line block are consecutive in it): the line
+    // block, hence the per-lane line table (two dependent global loads in a ragged batch), changes once per ~range
+    // instead of at nearly every tile as with CTA-strided items, and neighbouring tiles' halos come from L1/L2.
+    // (MUSAN-shaped corpus batch, k = 21: 0.68 -> see DESIGN.md ns per frame.)
+    const int64_t per_cta = (n_items + gridDim.x - 1) / gridDim.x;
+    const int64_t item_first = per_cta * blockIdx.x;
+    const int64_t n_lb = (n_lines + 31) >> 5;
+    const int64_t my_items = max((int64_t)0, min(per_cta, n_items - item_first));
 
     if (warp >= kComputeWarps) {
         // ===== loader warps =====
@@ -428,13 +462,14 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
         int b = 0;
         uint32_t bphase = 1;                               // parity of the buffer's previous release
         bool bfirst = true;
-        int64_t item = blockIdx.x;
-        for (int64_t n = 0; n < my_items; ++n, item += gridDim.x) {
+        int64_t item = item_first;
+        TileWalk tw;
+        for (int64_t n = 0; n < my_items; ++n, ++item) {
             int64_t lb;
             int p0;
-            if (tile_list != nullptr) {                    // ragged batch: explicit list of the tiles that exist
-                const int2 tl = __ldg(tile_list + item);
-                lb = tl.x; p0 = tl.y;
+            if (tile_first != nullptr) {                   // ragged batch: only the tiles that exist
+                tw.locate(tile_first, n_lb, item);
+                lb = tw.lb; p0 = (int)(item - tw.first) * TT;
             } else if (n_ptiles == 1) {
                 lb = item; p0 = 0;
             } else {
@@ -457,14 +492,15 @@ median_fast_kernel(const float* __restrict__ S, float* __restrict__ out, const i
         int64_t li_lb = -1;
         int b = warp % NB;
         uint32_t phase = (uint32_t)(warp / NB) & 1u;
-        int64_t item = blockIdx.x + (int64_t)warp * gridDim.x;
-        for (int64_t n = warp; n < my_items; n += kComputeWarps, item += (int64_t)kComputeWarps * gridDim.x) {
+        int64_t item = item_first + warp;
+        TileWalk tw;
+        for (int64_t n = warp; n < my_items; n += kComputeWarps, item += kComputeWarps) {
             float* sm = smem + (size_t)b * tile_floats;
             int64_t lb;
             int p0;
-            if (tile_list != nullptr) {                    // ragged batch: explicit list of the tiles that exist
-                const int2 tl = __ldg(tile_list + item);
-                lb = tl.x; p0 = tl.y;
+            if (tile_first != nullptr) {                   // ragged batch: only the tiles that exist
+                tw.locate(tile_first, n_lb, item);
+                lb = tw.lb; p0 = (int)(item - tw.first) * TT;
             } else if (n_ptiles == 1) {
                 lb = item; p0 = 0;
             } else {
@@ -716,30 +752,30 @@ median_generic_kernel(const float* __restrict__ S, float* __restrict__ out, cons
     }
 }
 
-// (line block, first position) of every time-axis tile that exists in a ragged batch; cached in the batch
-static int time_tile_list(hpss_ctx* ctx, const hpss_batch* cb, int rows, int TT, const int2** d_list, int64_t* n_tiles) {
+// tiles of a ragged batch: only those that exist, as a prefix count per line block (tile -> (line block, first position)
+// by TileWalk in the kernel); cached in the batch
+static int time_tile_list(hpss_ctx* ctx, const hpss_batch* cb, int rows, int TT, const int64_t** d_first, int64_t* n_tiles) {
     hpss_batch* b = const_cast<hpss_batch*>(cb);
     std::lock_guard<std::mutex> lk(ctx->mu);
     const auto key = std::make_pair(rows, TT);
     auto it = b->time_tiles.find(key);
     if (it == b->time_tiles.end()) {
-        std::vector<int2> tiles;
         const int64_t n_lines = (int64_t)b->n_clips * rows;
-        for (int64_t lb = 0; lb * 32 < n_lines; ++lb) {
+        const int64_t n_lb = (n_lines + 31) / 32;
+        std::vector<int64_t> first((size_t)n_lb + 1, 0);        // first[lb] = tiles of the line blocks before lb
+        for (int64_t lb = 0; lb < n_lb; ++lb) {
             const int c0 = (int)((lb * 32) / rows);
             const int c1 = (int)(std::min(n_lines - 1, lb * 32 + 31) / rows);
             int64_t tmax = 0;
             for (int c = c0; c <= c1; ++c) tmax = std::max(tmax, b->frame_off[c + 1] - b->frame_off[c]);
-            for (int64_t p0 = 0; p0 < tmax; p0 += TT) tiles.push_back(make_int2((int)lb, (int)p0));
+            first[lb + 1] = first[lb] + (tmax + TT - 1) / TT;
         }
-        int2* d = nullptr;
-        if (!tiles.empty()) {
-            HPSS_CUDA(cudaMalloc(&d, sizeof(int2) * tiles.size()));
-            HPSS_CUDA(cudaMemcpy(d, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice));
-        }
-        it = b->time_tiles.emplace(key, std::make_pair(d, (int64_t)tiles.size())).first;
+        int64_t* d = nullptr;
+        HPSS_CUDA(cudaMalloc(&d, sizeof(int64_t) * first.size()));
+        HPSS_CUDA(cudaMemcpy(d, first.data(), sizeof(int64_t) * first.size(), cudaMemcpyHostToDevice));
+        it = b->time_tiles.emplace(key, std::make_pair(d, first.back())).first;
     }
-    *d_list = it->second.first;
+    *d_first = it->second.first;
     *n_tiles = it->second.second;
     return HPSS_OK;
 }
@@ -767,8 +803,8 @@ int launch_fast(hpss_ctx* ctx, const hpss_batch* b, const float* S, float* out, 
     const int n_ptiles = (int)((max_len + TT - 1) / TT);
     const int64_t n_lb = (n_lines + 31) / 32;
     int64_t n_items = n_lb * n_ptiles;
-    const int2* tile_list = nullptr;
-    if (TIME_AXIS && uniform_T == 0 && n_ptiles > 1 && n_lines < 0x7fffffffLL * 32) {
+    const int64_t* tile_list = nullptr;
+    if (TIME_AXIS && uniform_T == 0 && n_ptiles > 1) {
         // ragged batch: only the tiles that exist (clips shorter than the longest have fewer)
         const int rc = time_tile_list(ctx, b, rows, TT, &tile_list, &n_items);
         if (rc) return rc;
