@@ -43,6 +43,8 @@ MEDIAN_CASES = [
     (201, [8], 21), (5, [8], 31), (40, [16], 16),           # multi-reflection, even k (generic path)
     (257, [300, 7, 131, 64], 17), (65, [33, 1, 2, 250], 63),
     (1025, [120], 31), (33, [70], 3), (33, [70], 5), (33, [70], 64), (17, [50], 101),
+    # ragged batches with several tiles per line: more tiles than CTAs, clips without frames, whole empty line blocks
+    (201, [3000, 17, 1500], 31), (40, [0, 0, 500, 0, 0, 0, 300], 21), (33, [0, 400, 0, 0, 5, 700, 0], 11),
 ]
 
 
