@@ -167,17 +167,21 @@ def stft_mag(batch: Batch, wave: torch.Tensor, n_fft: int, win_length: int, hop_
     return (S, cplx) if return_complex else S
 
 
-def median_time(batch: Batch, S: torch.Tensor, rows: int, k: int) -> torch.Tensor:
-    out = torch.empty_like(S)
+def median_time(batch: Batch, S: torch.Tensor, rows: int, k: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    out = torch.empty_like(S) if out is None else out
+    if out.numel() != S.numel():
+        raise ValueError("median_time: out must have the size of S")
     check(batch.lib.hpss_median_time(batch.ctx.handle, batch.handle, _dev_ptr(S, torch.float32, "S"), int(rows), int(k),
-                                     _dev_ptr(out), _stream_ptr()))
+                                     _dev_ptr(out, torch.float32, "out"), _stream_ptr()))
     return out
 
 
-def median_freq(batch: Batch, S: torch.Tensor, rows: int, k: int) -> torch.Tensor:
-    out = torch.empty_like(S)
+def median_freq(batch: Batch, S: torch.Tensor, rows: int, k: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    out = torch.empty_like(S) if out is None else out
+    if out.numel() != S.numel():
+        raise ValueError("median_freq: out must have the size of S")
     check(batch.lib.hpss_median_freq(batch.ctx.handle, batch.handle, _dev_ptr(S, torch.float32, "S"), int(rows), int(k),
-                                     _dev_ptr(out), _stream_ptr()))
+                                     _dev_ptr(out, torch.float32, "out"), _stream_ptr()))
     return out
 
 

@@ -445,6 +445,37 @@ def test_no_out_of_bounds_writes_canary(ctx):
         assert torch.equal(ref, out)
 
 
+@pytest.mark.parametrize("frames,rows,k", [([98] * 37, 201, 31), ([98] * 37, 201, 21), ([98] * 5, 201, 7), ([101] * 33, 64, 11),
+                                            ([3000, 17, 1500], 201, 21), ([700, 0, 5, 333], 33, 31), ([98, 60, 131], 201, 63),
+                                            ([50], 17, 101)])
+def test_median_outputs_stay_inside_their_buffers(ctx, frames, rows, k):
+    """Canaries around the outputs of both median axes for every kernel family: dense bulk-copy tiles (equal clips),
+    the cp.async ring with the prefix walk (ragged, several tiles per line), the register walk and the generic
+    rank-counting fallback.  The input sits between canaries too (a bulk copy that overran would read them: +inf
+    would show up in the medians)."""
+    rng = np.random.default_rng(len(frames) * 131 + k)
+    n = rows * int(sum(frames))
+    pad = 8192
+    big_in = torch.full((n + 2 * pad,), float("inf"), dtype=torch.float32, device="cuda")
+    x = np.abs(rng.standard_normal(n)).astype(np.float32)
+    big_in[pad:pad + n] = to_dev(x)
+    S = big_in[pad:pad + n]
+    batch = engine.Batch(ctx, clip_frames=frames)
+    for fn, axis in ((engine.median_time, 1), (engine.median_freq, 0)):
+        big = torch.full((n + 2 * pad,), float("nan"), dtype=torch.float32, device="cuda")
+        out = big[pad:pad + n]
+        fn(batch, S, rows, k, out=out)
+        torch.cuda.synchronize()
+        assert torch.isnan(big[:pad]).all() and torch.isnan(big[pad + n:]).all(), f"axis {axis}: canary overwritten"
+        assert torch.isfinite(out).all(), f"axis {axis}: read outside the input"
+        o = 0
+        got = out.cpu().numpy()
+        for T in frames:
+            m = x[o:o + rows * T].reshape(rows, T)
+            assert np.array_equal(got[o:o + rows * T].reshape(rows, T), lr.median_filter_1d(m, k, axis=axis))
+            o += rows * T
+
+
 def test_moments_uniform_more_than_four_classes(ctx):
     """moments_uniform_kernel with 6 classes (the 8-class instantiation)."""
     rng = np.random.default_rng(77)
