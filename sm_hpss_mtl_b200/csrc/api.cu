@@ -821,10 +821,11 @@ int hpss_pipeline_create(hpss_ctx* ctx, const int64_t* clip_len, int32_t n_clips
         }
         pl->frame_off[c + 1] = pl->frame_off[c] + 1 + (pl->wav_len[c] - p->n_fft) / p->hop_length;
     }
-    // chunking: ~16 chunks, at least 1 M samples each, never splitting a clip
+    // chunking: ~16 chunks, at least 1 M samples each, never splitting a clip;
     const int64_t total = pl->in_off[n_clips];
     const int n_target = n_chunks_hint > 0 ? n_chunks_hint : (knobs().host_chunks > 0 ? knobs().host_chunks : 16);
-    const int64_t target = std::max<int64_t>(total / n_target, 1 << 20);
+    // the last chunk is about half a chunk: its compute (and download) is the part of the pass no transfer hides
+    const int64_t target = std::max<int64_t>(n_target >= 2 ? (int64_t)((double)total / (n_target - 0.5)) + 1 : total, 1 << 20);
     pl->cut.assign(1, 0);
     for (int c = 0; c < n_clips;) {
         int e = c;
