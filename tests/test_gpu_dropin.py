@@ -213,6 +213,39 @@ def test_ragged_batch_musan_like(ctx):
         assert got.shape == want.shape and rel_l2(got, want) < TOL, c
 
 
+def test_corpus_shaped_batch_properties(ctx):
+    """BASELINE.json configs[2] shape at 1/8 scale (136 MUSAN-length clips, ~12 h, k = 21/11) in ONE ragged batch:
+    every selected clip must come out bit-identical to the same clip processed alone (a different tiling: the ragged
+    batch walks a tile prefix table over contiguous tile ranges, the single clip takes the uniform path), and the
+    medians of the shortest clip are checked against scipy."""
+    rng = np.random.default_rng(2024)
+    d = np.concatenate([rng.gamma(4.0, 232.0 / 4.0, size=83), rng.gamma(3.0, 511.0 / 3.0, size=53)])
+    lens = [int(x * 16000) for x in np.clip(d, 5.0, 1800.0)]
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    wave = torch.randn(int(offs[-1]), device="cuda", generator=g) * 0.2
+    wave += 0.4 * torch.sin(torch.arange(wave.numel(), device="cuda", dtype=torch.float32) * (2 * np.pi * 440.0 / 16000))
+    prm = engine.make_params(l_harm=21, l_perc=11, n_mels=120)
+    batch = engine.Batch(ctx, clip_lengths=lens, n_fft=400, hop_length=160)
+    out = engine.featuregram(batch, wave, prm)
+    assert torch.isfinite(out).all()
+    order = np.argsort(lens)
+    picks = sorted({0, len(lens) - 1, int(order[0]), int(order[-1]), int(order[len(order) // 2]), 17, 99})
+    for c in picks:
+        y = wave[offs[c]:offs[c + 1]].clone()
+        one = engine.Batch(ctx, clip_lengths=[lens[c]], n_fft=400, hop_length=160)
+        alone = engine.featuregram(one, y, prm)
+        assert torch.equal(batch.clip(out, 240, c).reshape(-1), alone), f"clip {c} ({lens[c]} samples)"
+    c = int(order[0])
+    S = engine.stft_mag(batch, wave, 400, 400, 160)
+    Sc = batch.clip(S, 201, c).cpu().numpy()
+    harm = batch.clip(engine.median_time(batch, S, 201, 21), 201, c).cpu().numpy()
+    perc = batch.clip(engine.median_freq(batch, S, 201, 11), 201, c).cpu().numpy()
+    assert np.array_equal(harm, lr.median_filter_scipy(Sc, 21, axis=1))
+    assert np.array_equal(perc, lr.median_filter_scipy(Sc, 11, axis=0))
+
+
 def test_one_hour_stream_full_size(ctx):
     """BASELINE.json configs[3] at full size: one 1-hour 16 kHz stream, n_fft 2048, hop 512, k = 31
     (112 497 frames x 1025 bins).  Medians bit-exact against scipy on row / column subsets (time-axis tiles
