@@ -25,6 +25,9 @@ namespace {
 #ifndef HPSS_WALK_MINB
 #define HPSS_WALK_MINB 4
 #endif
+#ifndef HPSS_WALKG_MINB
+#define HPSS_WALKG_MINB 4
+#endif
 constexpr int kWalkWarps = 4;
 
 // Addresses come from the FMA pipe (fma_pipe_* in common.cuh): an element of the lane's clip is clip_base[i0 + row * T]
@@ -37,8 +40,15 @@ __device__ __forceinline__ void store_elem(float* base, uint32_t idx, uint64_t f
     fma_pipe_store(base, idx, four, v);
 }
 
+// resident CTAs per SM the register allocation aims at: as many as fit without spilling (measured on the 4096 x 1 s
+// batch: k = 7 0.155 -> 0.135 ms at 12, k = 15 0.148 -> 0.138 ms at 8, k = 19 0.162 -> 0.155 ms at 6; one step more
+// spills and costs 30-90 %; k = 11 needs 60 registers either way)
+constexpr int walk_min_blocks(int K) {
+    return K > 47 ? 2 : K > 35 ? 3 : K <= 7 ? 12 : K <= 15 ? 8 : K <= 19 ? 6 : HPSS_WALK_MINB;
+}
+
 template <int K>
-__global__ void __launch_bounds__(kWalkWarps * 32, K > 35 ? (K > 47 ? 2 : 3) : HPSS_WALK_MINB)
+__global__ void __launch_bounds__(kWalkWarps * 32, walk_min_blocks(K))
 median_freq_walk_kernel(const float* __restrict__ S, float* __restrict__ perc, const int64_t* __restrict__ frame_off,
                         const int32_t* __restrict__ block_clip, int64_t total_frames, int rows) {
     using Step = MedianStep<K>;
@@ -136,7 +146,7 @@ median_freq_walk_kernel(const float* __restrict__ S, float* __restrict__ perc, c
 // inputs of a group live in registers, a group produces G outputs, the window then moves up by G rows (K - 1
 // register moves, G coalesced loads prefetched during the previous network).
 template <int K>
-__global__ void __launch_bounds__(kWalkWarps * 32, K > 43 ? 3 : 4)
+__global__ void __launch_bounds__(kWalkWarps * 32, K > 43 ? 3 : (K <= 17 ? 8 : HPSS_WALKG_MINB))   // (k = 17: 0.172 -> 0.160 ms at 8 CTAs per SM; 21 .. 29 do not move)
 median_freq_walk_group_kernel(const float* __restrict__ S, float* __restrict__ perc, const int64_t* __restrict__ frame_off,
                               const int32_t* __restrict__ block_clip, int64_t total_frames, int rows) {
     constexpr int G = MedianGroup<K>::G;
